@@ -1,0 +1,137 @@
+/*
+ * gotoh_b200.h - C ABI of libgotoh_b200.so, the B200-native (sm_100a CUDA) replacement
+ * for MiCall-Lite's Gotoh aligner hot path.
+ *
+ * What it replaces.  The reference exposes this path only as a CPython extension
+ * ("gotoh", /root/reference/micall/alignment/gotoh.cpp:729-739) with three callables:
+ *     align_it      (gotoh.cpp:624-658)   nt,  init_pairscore(5,4)
+ *     align_it_aa   (gotoh.cpp:660-693)   aa,  init_pairscore_hiv25()
+ *     align_it_aa_rb(gotoh.cpp:695-727)   aa,  init_pairscore_aa(4,-2), degap, term=0
+ * all three being: score-table init -> trim -> align() (gotoh.cpp:233-527) -> two strings
+ * and a score.  There is no C ABI in the reference; this header is the FFI a maintainer
+ * would bind instead (ctypes stub shown in INTEGRATION.md).  Plain pointers and sizes
+ * only; the caller owns every input and output buffer; nothing returned is owned by the
+ * library except opaque plan handles.
+ *
+ * No CPU fallback exists: every compute entry point fails with GOTOH_B200_ENODEVICE when
+ * no CUDA device is usable.
+ */
+#ifndef GOTOH_B200_H
+#define GOTOH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOTOH_B200_VERSION 100 /* 0.1.0 */
+
+/* matrix_id: which of the reference's table initialisers applies (gotoh.cpp:26-213). */
+enum {
+    GOTOH_B200_NT = 0,    /* align_it:       init_pairscore(5,4)          gotoh.cpp:637 */
+    GOTOH_B200_HIV25 = 1, /* align_it_aa:    init_pairscore_hiv25()       gotoh.cpp:673 */
+    GOTOH_B200_AA_RB = 2  /* align_it_aa_rb: init_pairscore_aa(4,-2), inputs degapped,
+                             use_terminal forced to 0          gotoh.cpp:707-718 */
+};
+
+/* Return codes (0 = success).  The reference has no error path after argument parsing
+ * (gotoh.cpp:633-635); inputs outside its defined domain are undefined behaviour there
+ *  and are rejected here instead. */
+enum {
+    GOTOH_B200_OK = 0,
+    GOTOH_B200_EINVAL = -1,    /* bad argument (NULL pointer, negative count, bad matrix_id ...) */
+    GOTOH_B200_EEMPTY = -2,    /* a sequence is empty after trim/degap: trim() reads seq[size-1], gotoh.cpp:555 */
+    GOTOH_B200_EDOMAIN = -3,   /* a byte outside 1..126: pairscore() index, gotoh.cpp:216-219 */
+    GOTOH_B200_ESENTINEL = -4, /* 2*gip+(max(M,N)+1)*gep >= 100000: boundary scores could fall below the
+                                  -100000 sentinel, gotoh.cpp:284-286 (uninitialised maxij/maxji) */
+    GOTOH_B200_ERANGE = -5,    /* output stride < M+N, lengths/penalties outside int32-safe range */
+    GOTOH_B200_ENODEVICE = -6, /* no usable CUDA device / device index not present */
+    GOTOH_B200_ECUDA = -7,     /* CUDA runtime error (message in gotoh_b200_last_error) */
+    GOTOH_B200_ENOMEM = -8     /* host or device allocation failed */
+};
+
+/* Library / device info. */
+int32_t gotoh_b200_version(void);
+/* Thread-local, NUL-terminated description of the last failure on this thread. */
+const char* gotoh_b200_last_error(void);
+/* Number of visible CUDA devices (0 if none / driver missing). */
+int32_t gotoh_b200_device_count(void);
+
+/* The score table exactly as the reference's pairscore() (gotoh.cpp:216-219) returns it
+ * after init_pairscore(5,4) / init_pairscore_hiv25() / init_pairscore_aa(4,-2):
+ * out[a*127+b] for a,b in 0..126.  Host-side builder, the same one the device tables are
+ * uploaded from. */
+int32_t gotoh_b200_pairscore_table(int32_t matrix_id, int32_t* out_127x127);
+
+/*
+ * One-shot batched alignment: host buffers in, host buffers out.  This is the batched
+ * form of align_it / align_it_aa / align_it_aa_rb: pair k aligns
+ *     standard = ref_bytes[ref_off[r] .. ref_off[r+1])   with r = ref_idx ? ref_idx[k] : k
+ *     seq      = qry_bytes[qry_off[k] .. qry_off[k+1])
+ * with the wrapper semantics of gotoh.cpp:624-727 (trim of " \t\n\r" on both, degap for
+ * AA_RB).  Results for pair k:
+ *     out_ref[out_off[k] .. +out_len[k])  aligned standard   (gotoh.cpp:650 1st string)
+ *     out_qry[out_off[k] .. +out_len[k])  aligned seq        (2nd string)
+ *     out_score[k]                        alignment score    (3rd value)
+ * out_off[k+1]-out_off[k] must be >= M_k+N_k (trimmed lengths); bytes past out_len[k] are
+ * left untouched.  No NUL terminators are written.
+ *
+ * n_refs    number of references (ref_off has n_refs+1 entries)
+ * ref_idx   per-pair reference index, or NULL when n_refs == n_pairs and pair k uses ref k
+ * device_mask  bit d set => shard onto CUDA device d (0 => device 0 only).  Pairs are
+ *           statically partitioned by cell count; there is no inter-device traffic.
+ */
+int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
+                               const int32_t* ref_idx,
+                               const uint8_t* qry_bytes, const int64_t* qry_off, int64_t n_pairs,
+                               int32_t gip, int32_t gep, int32_t use_terminal, int32_t matrix_id,
+                               uint8_t* out_ref, uint8_t* out_qry, const int64_t* out_off,
+                               int32_t* out_len, int32_t* out_score, uint32_t device_mask);
+
+/*
+ * Staged form of the same call, for callers that keep data resident in HBM or want the
+ * device time of each phase:
+ *   plan_create  validate + trim + bucket + pack on the host, allocate HBM, copy inputs H2D
+ *   plan_run     forward DP + traceback + string emit on the device; results stay in HBM.
+ *                Re-runnable; *device_ms (optional) = CUDA-event time of this run on the
+ *                plan's stream, *forward_ms (optional) = the forward-DP kernels alone.
+ *   plan_fetch   copy results D2H into caller buffers (same meaning as align_batch)
+ *   plan_destroy release everything
+ * A plan is bound to one device and must be used by one host thread at a time.
+ */
+typedef struct gotoh_b200_plan gotoh_b200_plan;
+
+int32_t gotoh_b200_plan_create(int32_t device,
+                               const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
+                               const int32_t* ref_idx,
+                               const uint8_t* qry_bytes, const int64_t* qry_off, int64_t n_pairs,
+                               int32_t gip, int32_t gep, int32_t use_terminal, int32_t matrix_id,
+                               const int64_t* out_off, gotoh_b200_plan** plan_out);
+int32_t gotoh_b200_plan_run(gotoh_b200_plan* plan, float* device_ms, float* forward_ms);
+int32_t gotoh_b200_plan_fetch(gotoh_b200_plan* plan, uint8_t* out_ref, uint8_t* out_qry,
+                              int32_t* out_len, int32_t* out_score);
+void gotoh_b200_plan_destroy(gotoh_b200_plan* plan);
+
+/* Introspection of a plan (for benchmarks and tests).  what:
+ *   0 total DP cells (sum M*N)          1 kernel launches per plan_run
+ *   2 bytes copied H2D by plan_create   3 bytes copied D2H by plan_fetch
+ *   4 direction-arena bytes in HBM      5 pairs on the 16-bit x2 path
+ *   6 pairs on the 32-bit path          7 number of arena chunks per run */
+int64_t gotoh_b200_plan_stat(const gotoh_b200_plan* plan, int32_t what);
+
+/* Pinned (page-locked) host memory for callers that want full-rate H2D/D2H copies. */
+void* gotoh_b200_host_alloc(int64_t bytes);
+void gotoh_b200_host_free(void* p);
+
+/* Integer-issue microbenchmark used for the roofline denominator ("peak
+ * INT32 issue must be measured").  Runs `which` (0 IADD3, 1 VIMNMX, 2 VIADDMNMX,
+ * 3 VIADDMNMX.S16x2, 4 VIMNMX3, 5 IMAD, 6 LOP3, 7 mixed ALU+IMAD, 8 forward-DP cell mix)
+ * on `device` and returns giga warp-instructions... see DESIGN.md; result in
+ * *ginstr_per_s (thread-level instructions per second / 1e9). */
+int32_t gotoh_b200_int_peak(int32_t device, int32_t which, double* ginstr_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOTOH_B200_H */

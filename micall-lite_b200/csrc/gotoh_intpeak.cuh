@@ -1,0 +1,133 @@
+// gotoh_intpeak.cuh - measured integer-issue peaks for the roofline denominator.
+//
+// the forward DP is bound by integer ALU issue, and "peak INT32 issue must be
+// measured on the box".  Each kernel below keeps 8 independent dependency chains per thread
+// busy with ONE instruction class (or the exact per-cell instruction mix of k_forward) and
+// reports thread-level instructions per second.  ILP 8 x 8 warps/SMSP hides the 4-cycle ALU
+// latency, so the result is the issue-rate ceiling of that class on the whole chip.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+
+namespace gotoh {
+namespace intpeak {
+
+enum {
+    W_ADD = 0, W_MNMX = 1, W_ADDMNMX = 2, W_ADDMNMX16 = 3, W_MNMX3 = 4, W_IMAD = 5, W_LOP3 = 6,
+    W_MIX_ALU_IMAD = 7, W_CELL16 = 8, W_CELL32 = 9, W_VADD2 = 10, W_SHFL = 11, W_MNMX3_16 = 12, W_COUNT = 13
+};
+
+template <int W>
+struct Ops { enum { PER_ITER = 1 }; };
+template <> struct Ops<W_MIX_ALU_IMAD> { enum { PER_ITER = 2 }; };
+template <> struct Ops<W_CELL16> { enum { PER_ITER = 7 }; };
+template <> struct Ops<W_CELL32> { enum { PER_ITER = 7 }; };
+
+template <int W>
+__global__ void __launch_bounds__(256) k_peak(int* out, int iters, int b, int c) {
+    unsigned x[8], y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x[j] = threadIdx.x * 7u + j * 13u + (unsigned)b; y[j] = threadIdx.x * 3u + j; }
+    const unsigned ub = (unsigned)b, uc = (unsigned)c;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (W == W_ADD) x[j] = x[j] + ub;
+                else if (W == W_MNMX) { const int m = max((int)x[j], (int)y[j]); y[j] = x[j]; x[j] = (unsigned)m; }
+                else if (W == W_ADDMNMX) x[j] = (unsigned)__viaddmax_s32((int)x[j], b, c);
+                else if (W == W_ADDMNMX16) x[j] = __viaddmax_s16x2(x[j], ub, uc);
+                else if (W == W_MNMX3) x[j] = (unsigned)__vimax3_s32((int)x[j], (int)x[(j + 1) & 7], (int)y[j]);
+                else if (W == W_MNMX3_16) x[j] = __vimax3_s16x2(x[j], x[(j + 1) & 7], y[j]);
+                else if (W == W_IMAD) x[j] = x[j] * ub + uc;
+                else if (W == W_LOP3) x[j] = (x[j] & ub) ^ y[j];
+                else if (W == W_VADD2) x[j] = __vadd2(x[j], ub);
+                else if (W == W_SHFL) x[j] = __shfl_up_sync(0xffffffffu, x[j], 1);
+                else if (W == W_MIX_ALU_IMAD) { x[j] = (unsigned)__viaddmax_s32((int)x[j], b, c); y[j] = y[j] * ub + uc; }
+                else if (W == W_CELL16) {
+                    // the per-cell mix of k_forward<Vec16>: 2 VIADDMNMX.S16x2, VIADD.16x2, VIMNMX3.S16x2,
+                    // LOP3 and two IMADs (x: running S, y: direction accumulator)
+                    const unsigned q = __viaddmax_s16x2(x[j], ub, y[j]);
+                    const unsigned p = __viaddmax_s16x2(x[(j + 1) & 7], uc, q);
+                    const unsigned d = __vadd2(x[(j + 2) & 7], ub);
+                    const unsigned C = __vimax3_s16x2(d, p, q);
+                    x[j] = C & 0xfffcfffcu;
+                    y[j] = (y[j] * 4u + C) - (x[j] * 4u + uc);
+                } else if (W == W_CELL32) {
+                    const int q = __viaddmax_s32((int)x[j], b, (int)y[j]);
+                    const int p = __viaddmax_s32((int)x[(j + 1) & 7], c, q);
+                    const int d = (int)x[(j + 2) & 7] + b;
+                    const int C = __vimax3_s32(d, p, q);
+                    x[j] = (unsigned)(C & ~3);
+                    y[j] = (y[j] * 4u + (unsigned)C) - (x[j] * 4u + uc);
+                }
+            }
+        }
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += x[j] ^ y[j];
+    if (s == 0x12345678u) out[0] = (int)s;   // keeps the chains live; practically never true
+}
+
+template <int W>
+int run_one(double* ginstr, char* err, size_t errlen) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        snprintf(err, errlen, "int_peak: cannot query device");
+        return -7;
+    }
+    int* d_out = nullptr;
+    if (cudaMalloc(&d_out, sizeof(int)) != cudaSuccess) { snprintf(err, errlen, "int_peak: cudaMalloc failed"); return -8; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = prop.multiProcessorCount * 8, block = 256;
+#ifdef GOTOH_SIMT_EMU
+    const int iters = 2;
+#else
+    const int iters = 2048;
+#endif
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, 0);
+        GOTOH_LAUNCH((k_peak<W>), dim3(grid), dim3(block), 0, (cudaStream_t)0, d_out, iters, 3 + rep, -5);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    if (cudaGetLastError() != cudaSuccess) { snprintf(err, errlen, "int_peak: kernel failed"); return -7; }
+    const double n = (double)grid * block * (double)iters * 4.0 * 8.0 * Ops<W>::PER_ITER;
+    *ginstr = best > 0.f ? n / (best * 1e-3) / 1e9 : 0.0;
+    return 0;
+}
+
+inline int run(int which, double* ginstr, char* err, size_t errlen) {
+    switch (which) {
+        case W_ADD: return run_one<W_ADD>(ginstr, err, errlen);
+        case W_MNMX: return run_one<W_MNMX>(ginstr, err, errlen);
+        case W_ADDMNMX: return run_one<W_ADDMNMX>(ginstr, err, errlen);
+        case W_ADDMNMX16: return run_one<W_ADDMNMX16>(ginstr, err, errlen);
+        case W_MNMX3: return run_one<W_MNMX3>(ginstr, err, errlen);
+        case W_IMAD: return run_one<W_IMAD>(ginstr, err, errlen);
+        case W_LOP3: return run_one<W_LOP3>(ginstr, err, errlen);
+        case W_MIX_ALU_IMAD: return run_one<W_MIX_ALU_IMAD>(ginstr, err, errlen);
+        case W_CELL16: return run_one<W_CELL16>(ginstr, err, errlen);
+        case W_CELL32: return run_one<W_CELL32>(ginstr, err, errlen);
+        case W_VADD2: return run_one<W_VADD2>(ginstr, err, errlen);
+        case W_SHFL: return run_one<W_SHFL>(ginstr, err, errlen);
+        case W_MNMX3_16: return run_one<W_MNMX3_16>(ginstr, err, errlen);
+    }
+    snprintf(err, errlen, "int_peak: unknown class %d", which);
+    return -1;
+}
+
+}  // namespace intpeak
+}  // namespace gotoh

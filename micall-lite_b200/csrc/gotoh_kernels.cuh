@@ -1,0 +1,562 @@
+// gotoh_kernels.cuh - sm_100a kernels for MiCall-Lite's Gotoh aligner hot path
+// (reference: /root/reference/micall/alignment/gotoh.cpp:233-527).
+//
+//   k_forward<V,K>  K1/K2/K3: affine-gap forward DP, one warp per task, anti-diagonal
+//                   wavefront across the 32 lanes (lane l owns K query columns and is one
+//                   reference row behind lane l-1), register-resident S/P/Q, shuffle
+//                   hand-off, 2-bit directions packed and stored coalesced, end-cell
+//                   selection fused into the epilogue.   (gotoh.cpp:288-450)
+//   k_walk          K4a: pointer-chase of the packed directions, one thread per pair,
+//                   emits a 2-bit op script + the terminal-gap score fix-up. (gotoh.cpp:452-510)
+//   k_emit          K4b: expands the op script into the two aligned strings with
+//                   coalesced stores, one warp per pair.                    (gotoh.cpp:436-513)
+//
+// Arithmetic is exact integer arithmetic; the two "vector" policies below only differ in
+// how many alignments share a 32-bit register:
+//   Vec32  one alignment per warp, int32 cells      (any length, any score range)
+//   Vec16  two alignments per warp, int16x2 cells    (VIADDMNMX.S16x2 / VIMNMX3.S16x2; host
+//          proves the score range fits before choosing it - see plan.cpp "range proof")
+//
+// Frames: with g = gep, u = -gip every stored value is
+//   X^(i,j) = 4 * ( X(i,j) + (i - base(i) + j) * g ) + tag,   tag: D=0, P=1, Q=2
+// The (i+j)*g shift removes the "+v" from both gap recurrences (gotoh.cpp:305-314); the
+// factor 4 and the tags make max3() of the three candidates carry the reference's
+// tie-break LEFT > UP > DIAG (gotoh.cpp:362-395) in its two low bits, which ARE the
+// direction code.  base(i) = R*floor(i/R) keeps int16 in range (Vec16 only).
+#pragma once
+
+#include <stdint.h>
+
+#ifndef GOTOH_SIMT_EMU
+#include <cuda_runtime.h>
+#define GOTOH_LAUNCH(kern, grid, block, smem, stream, ...)            \
+    do {                                                              \
+        auto _gotoh_k = kern;                                         \
+        _gotoh_k<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+    } while (0)
+#define GOTOH_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+namespace gotoh {
+
+enum { DIR_DIAG = 0, DIR_UP = 1, DIR_LEFT = 2 };
+enum { FWD_WARPS = 4 };          // warps per CTA in k_forward
+enum { REF_PAD = 64 };           // class bytes of padding on both sides of every reference
+enum { PAD_CLASS = 0 };
+
+// One alignment (pair), in plan order.  64 bytes.
+struct PairInfo {
+    int64_t ref_pos;   // index of row 1's byte in d_ref_raw / d_ref_cls (both carry REF_PAD padding)
+    int64_t qry_pos;   // index of column 1's byte in d_qry
+    int64_t dir_off;   // first uint4 of this pair's (task's) direction arena
+    int64_t out_off;   // first output byte (caller's out_off[orig])
+    int32_t M, N;      // trimmed lengths: rows (standard) and columns (seq)
+    int32_t nblk;      // step blocks per strip in the arena
+    int32_t ops_off;   // first uint32 of this pair's op script
+    int16_t K;         // query columns per lane
+    int8_t x2;         // 1: Vec16 arena (32 dir bits per lane-step, two alignments)
+    int8_t half;       // which half of the Vec16 word belongs to this pair
+    int32_t orig;      // caller's pair index
+    int32_t pad0, pad1;
+};
+
+struct Task {          // one warp's work item
+    int32_t pair_a;
+    int32_t pair_b;    // -1: none (Vec32, or odd leftover in Vec16)
+};
+
+struct FwdParams {
+    const PairInfo* pairs;
+    const Task* tasks;
+    int32_t task_first, task_count;
+    const uint8_t* ref_cls;     // class index per reference position (0 = padding class)
+    const uint8_t* qry;
+    const int32_t* table4;      // [ncls][128] : 4*(T[rep(c)][b] + 2*gep), row 0 unused
+    int32_t ncls;               // number of classes incl. the padding class 0
+    int32_t gip, gep;
+    int32_t rebase_mask;        // Vec16: R-1 (R power of two); Vec32: unused
+    int32_t smin_m1;            // Vec16: lower bound of any true score, minus 1 (tracking seed)
+    uint4* dir;                 // direction arena
+    int2* bnd;                  // Vec32 multi-strip boundary columns: [task_slot][2][bnd_stride]
+    int64_t bnd_stride;
+    int32_t* score;             // per pair: S at the chosen end cell (before terminal fix-up)
+    int32_t* end_i;
+    int32_t* end_j;
+    uint32_t* work_counter;     // dynamic task scheduler
+};
+
+// ------------------------------------------------------------------------------------
+// Vector policies
+// ------------------------------------------------------------------------------------
+struct Vec32 {
+    typedef int T;
+    enum { NPAIR = 1, STEPS = 8 };  // STEPS lane-steps fill one uint4 of directions
+    static __device__ __forceinline__ T addmax(T a, T b, T c) { return __viaddmax_s32(a, b, c); }
+    static __device__ __forceinline__ T max3(T a, T b, T c) { return __vimax3_s32(a, b, c); }
+    static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    static __device__ __forceinline__ T clr(T c) { return c & ~3; }
+    static __device__ __forceinline__ T both(int x) { return x; }
+    static __device__ __forceinline__ T pack(int lo, int) { return lo; }
+    static __device__ __forceinline__ int lo(T v) { return v; }
+    static __device__ __forceinline__ int hi(T v) { return v; }
+    static __device__ __forceinline__ unsigned raw(T v) { return (unsigned)v; }
+};
+
+struct Vec16 {
+    typedef unsigned T;
+    enum { NPAIR = 2, STEPS = 4 };
+    static __device__ __forceinline__ T addmax(T a, T b, T c) { return __viaddmax_s16x2(a, b, c); }
+    static __device__ __forceinline__ T max3(T a, T b, T c) { return __vimax3_s16x2(a, b, c); }
+    static __device__ __forceinline__ T add(T a, T b) { return __vadd2(a, b); }
+    static __device__ __forceinline__ T clr(T c) { return c & 0xfffcfffcu; }
+    static __device__ __forceinline__ T pack(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+    static __device__ __forceinline__ T both(int x) { return pack(x, x); }
+    static __device__ __forceinline__ int lo(T v) { return (int)(short)(v & 0xffffu); }
+    static __device__ __forceinline__ int hi(T v) { return (int)(short)(v >> 16); }
+    static __device__ __forceinline__ unsigned raw(T v) { return v; }
+};
+
+// Location of the 2-bit direction of cell (i,j) (1-based) inside a pair's arena.
+// Arena layout: [strip][step block][lane] uint4; one uint4 = STEPS lane-steps.
+//   Vec32: 16 bits per lane-step, two steps per 32-bit word (even step in the low half)
+//   Vec16: 32 bits per lane-step, low half = pair_a, high half = pair_b
+// Inside a 16-bit field, column k of the lane sits at bits [2(K-1-k)+1 : 2(K-1-k)].
+struct DirAddr {
+    int64_t word;   // index in uint32 units from the arena base
+    int shift;
+};
+__device__ __forceinline__ DirAddr dir_addr(const PairInfo& p, int i, int j) {
+    const int K = p.K;
+    const int jj = j - 1;
+    const int strip = jj / (32 * K);
+    const int r = jj - strip * 32 * K;
+    const int lane = r / K;
+    const int k = r - lane * K;
+    const int tt = i + lane - 1;  // step index, 0-based
+    DirAddr a;
+    if (p.x2) {
+        const int tb = tt >> 2, s = tt & 3;
+        a.word = ((p.dir_off + ((int64_t)strip * p.nblk + tb) * 32 + lane) << 2) + s;
+        a.shift = 16 * p.half + 2 * (K - 1 - k);
+    } else {
+        const int tb = tt >> 3, s = tt & 7;
+        a.word = ((p.dir_off + ((int64_t)strip * p.nblk + tb) * 32 + lane) << 2) + (s >> 1);
+        a.shift = 16 * (s & 1) + 2 * (K - 1 - k);
+    }
+    return a;
+}
+
+// ------------------------------------------------------------------------------------
+// K1/K2/K3  forward DP
+// ------------------------------------------------------------------------------------
+#define GOTOH_ROW0_INIT()                                                                          \
+    do {                                                                                           \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) {                                            \
+            /* S(0,j) = 0 and P(0,j) = 0 (gotoh.cpp:267-272) in the frame: 4*j*g (+1 tag for P);  \
+               padding columns clone column N */                                                   \
+            const int ja_ = min(j0 + k + 1, Na), jb_ = min(j0 + k + 1, Nb);                        \
+            S[k] = V::pack(ja_ * g4, jb_ * g4);                                                    \
+            P[k] = V::pack(ja_ * g4 + 1, jb_ * g4 + 1);                                            \
+        }                                                                                          \
+        Sd_in = V::pack(min(j0, Na) * g4, min(j0, Nb) * g4); /* S^(0, j0) */                       \
+        diag0 = V::both(0);                                  /* 4*(i-1)*g at i = 1 */              \
+        /* seed below any reachable score, expressed in the row-0 frame of column N */             \
+        lastcol_best_a = 4 * p.smin_m1 + Na * g4;                                                  \
+        lastcol_best_b = 4 * p.smin_m1 + Nb * g4;                                                  \
+    } while (0)
+
+template <class V, int K>
+struct FwdSmem {
+    enum { K4 = (K + 3) / 4 };
+    // profile: [class][K4][lane] of 4 packed entries (int4 for Vec32, uint4 for Vec16)
+    static __host__ __device__ size_t per_warp(int ncls) { return (size_t)ncls * K4 * 32 * 16 + 2 * 32 * sizeof(int2); }
+};
+
+template <class V, int K>
+__global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
+    typedef typename V::T T;
+    enum { K4 = (K + 3) / 4, STEPS = V::STEPS, NP = V::NPAIR };
+    GOTOH_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* my_smem = smem_raw + (size_t)warp * FwdSmem<V, K>::per_warp(p.ncls);
+    uint4* prof = reinterpret_cast<uint4*>(my_smem);
+    int2* ring = reinterpret_cast<int2*>(my_smem + (size_t)p.ncls * K4 * 32 * 16);  // [2][32]
+
+    const int g4 = 4 * p.gep;
+    const int u4 = -4 * p.gip;
+    const T c_up = V::both(u4 + 1);          // P^ = max(S^up + 4u+1, P^up)
+    const T c_sl0 = V::both(u4);             // column 0 seen by the Q recurrence: s~ = u      (gotoh.cpp:291)
+    const T c_q0 = V::both(2 * u4 + 2);      //                                     q~ = 2u     (gotoh.cpp:293)
+    const T c_g4 = V::both(g4);
+
+    for (;;) {
+        // ---- dynamic task fetch (one atomic per warp) ---------------------------------
+        unsigned tsk = 0;
+        if (lane == 0) tsk = atomicAdd(p.work_counter, 1u);
+        tsk = __shfl_sync(0xffffffffu, tsk, 0);
+        if (tsk >= (unsigned)p.task_count) break;
+        const Task task = p.tasks[p.task_first + tsk];
+        const PairInfo pa = p.pairs[task.pair_a];
+        const PairInfo pb = p.pairs[task.pair_b >= 0 ? task.pair_b : task.pair_a];
+        const int M = pa.M;                       // both halves share the reference
+        const int Na = pa.N, Nb = (NP == 2) ? pb.N : pa.N;
+        const int Nmax = Na > Nb ? Na : Nb;
+        const int nstrips = (Nmax + 32 * K - 1) / (32 * K);   // Vec16 tasks always have 1
+        const int nblk = pa.nblk;
+        const uint8_t* cls = p.ref_cls + pa.ref_pos;          // cls[i-1] = class of row i
+        const uint8_t* qa = p.qry + pa.qry_pos;
+        const uint8_t* qb = p.qry + pb.qry_pos;
+        int2* bnd0 = p.bnd + ((int64_t)(blockIdx.x * FWD_WARPS + warp) * 2) * p.bnd_stride;  // unused when nstrips == 1
+
+        // running best of the last column (largest i wins ties, gotoh.cpp:406-410) - every
+        // lane tracks its own last register; the owner lane's copy is read in the epilogue
+        int lastcol_best_a = 0, lastcol_i_a = 0, lastcol_best_b = 0, lastcol_i_b = 0;
+        // best of the last row (largest j wins ties, gotoh.cpp:399-403)
+        int lastrow_best_a = -2147483647, lastrow_j_a = 0, lastrow_best_b = -2147483647, lastrow_j_b = 0;
+
+        for (int strip = 0; strip < nstrips; ++strip) {
+            const int j0 = (strip * 32 + lane) * K;           // columns j0+1 .. j0+K (1-based)
+            const bool last_strip = (strip == nstrips - 1);
+            int2* bnd_in = bnd0 + (int64_t)((strip + 1) & 1) * p.bnd_stride;
+            int2* bnd_out = bnd0 + (int64_t)(strip & 1) * p.bnd_stride;
+
+            // ---- query profile for this strip: prof[c][k4][lane].{x,y,z,w} -------------
+            __syncwarp();
+            T Uq[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int ja = j0 + k;
+                const bool real_a = ja < Na, real_b = ja < Nb;
+                Uq[k] = V::pack(real_a ? u4 + 2 : 3, real_b ? u4 + 2 : 3);
+            }
+            for (int c = 0; c < p.ncls; ++c) {
+                const int32_t* trow = p.table4 + c * 128;
+#pragma unroll
+                for (int kq = 0; kq < K4; ++kq) {
+                    unsigned e[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int ja = j0 + kq * 4 + kk;
+                        // padding columns (beyond N) use E = 4u so that they clone column N
+                        const int ea = (ja < Na) ? (int)trow[qa[ja]] : u4;
+                        const int eb = (NP == 2) ? ((ja < Nb) ? (int)trow[qb[ja]] : u4) : 0;
+                        e[kk] = V::raw(V::pack(ea, eb));
+                    }
+                    prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
+                }
+            }
+            __syncwarp();
+
+            // ---- lane state -----------------------------------------------------------
+            T S[K], P[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { S[k] = V::both(0); P[k] = V::both(0); }
+            T sendS = V::both(0), sendQ = V::both(0);  // what lane+1 consumes next step
+            T Sd_in = V::both(0);                       // S^(i-1, j0): diagonal input of column j0+1
+            T diag0 = V::both(0);                       // lane 0 / strip 0: "S(i-1,0) = 0" (gotoh.cpp:292) in frame
+            uint4 dwords = make_uint4(0, 0, 0, 0);
+            GOTOH_ROW0_INIT();   // lane 0 starts at row 1 in the very first step
+
+            int next_cls = cls[-lane];                  // class of row i = 1 - lane (padding when i < 1)
+
+            for (int tb = 0; tb < nblk; ++tb) {
+#pragma unroll
+                for (int s = 0; s < STEPS; ++s) {
+                    const int t = tb * STEPS + s + 1;   // 1-based step
+                    const int i = t - lane;             // this lane's row
+                    const int my_cls = next_cls;
+                    next_cls = cls[i];                  // row i+1 (prefetch; padded on both sides)
+
+                    // ---- hand-off from the left neighbour (its row i, produced last step)
+                    T Sl = __shfl_up_sync(0xffffffffu, sendS, 1);
+                    T Ql = __shfl_up_sync(0xffffffffu, sendQ, 1);
+                    if (strip > 0) {
+                        // boundary column written by the previous strip; staged 32 rows at a time
+                        if (((t - 1) & 31) == 0) {
+                            __syncwarp();
+                            const int row = t + lane;   // lane 0 is at row t+l at step t+l
+                            int2 b = make_int2(0, 0);
+                            if (row >= 1 && row <= M) b = bnd_in[row];
+                            ring[(((t - 1) >> 5) & 1) * 32 + lane] = b;
+                            __syncwarp();
+                        }
+                        if (lane == 0) {
+                            const int2 b = ring[(((t - 1) >> 5) & 1) * 32 + ((t - 1) & 31)];
+                            Sl = (T)b.x; Ql = (T)b.y;
+                        }
+                    } else if (lane == 0) {
+                        Sl = c_sl0; Ql = c_q0;
+                    }
+                    T sdiag = Sd_in;
+                    if (strip == 0 && lane == 0) sdiag = diag0;
+
+                    // ---- int16 range control: rebase every R rows (Vec16 only) ---------
+                    if (NP == 2) {
+                        if (i > 0 && (i & p.rebase_mask) == 0) {
+                            const T d = V::both(-(p.rebase_mask + 1) * g4);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) { S[k] = V::add(S[k], d); P[k] = V::add(P[k], d); }
+                            sdiag = V::add(sdiag, d);
+                            diag0 = V::add(diag0, d);
+                            lastcol_best_a += -(p.rebase_mask + 1) * g4;  // tracked in the stored frame
+                            lastcol_best_b += -(p.rebase_mask + 1) * g4;
+                        }
+                    }
+                    Sd_in = Sl;
+
+                    // ---- K cells of row i ------------------------------------------------
+                    const uint4* prow = prof + (my_cls * K4) * 32 + lane;
+                    T sleft = Sl, q = Ql;
+                    unsigned accC = 0, accS = 0;
+#pragma unroll
+                    for (int kq = 0; kq < K4; ++kq) {
+                        const uint4 e4 = prow[kq * 32];
+                        const unsigned ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int k = kq * 4 + kk;
+                            if (k < K) {
+                                q = V::addmax(sleft, Uq[k], q);            // Q^ (gotoh.cpp:305-308)
+                                const T pp = V::addmax(S[k], c_up, P[k]);  // P^ (gotoh.cpp:311-314)
+                                const T d = V::add(sdiag, (T)ev[kk]);      // D^ (gotoh.cpp:319)
+                                const T C = V::max3(d, pp, q);             // select (gotoh.cpp:362-395)
+                                sdiag = S[k];
+                                P[k] = pp;
+                                S[k] = V::clr(C);
+                                sleft = S[k];
+                                accC = accC * 4u + V::raw(C);
+                                accS = accS * 4u + V::raw(S[k]);
+                            }
+                        }
+                    }
+                    sendS = S[K - 1];
+                    sendQ = q;
+                    diag0 = V::add(diag0, c_g4);
+
+                    // ---- directions: 2K bits per alignment per lane-step -----------------
+                    const unsigned dstep = accC - accS;
+                    if (NP == 2) {
+                        if (s == 0) dwords.x = dstep; else if (s == 1) dwords.y = dstep;
+                        else if (s == 2) dwords.z = dstep; else dwords.w = dstep;
+                    } else {
+                        const unsigned sh = dstep << (16 * (s & 1));
+                        if ((s >> 1) == 0) dwords.x = (s & 1) ? (dwords.x | sh) : sh;
+                        else if ((s >> 1) == 1) dwords.y = (s & 1) ? (dwords.y | sh) : sh;
+                        else if ((s >> 1) == 2) dwords.z = (s & 1) ? (dwords.z | sh) : sh;
+                        else dwords.w = (s & 1) ? (dwords.w | sh) : sh;
+                    }
+
+                    // ---- last column: running max, ties -> larger i (gotoh.cpp:406-410) ---
+                    // tracked in the stored frame of the current row: carrying a score one row
+                    // down adds 4g.  Padding columns clone column N, so S[K-1] of the owner lane
+                    // is S^(i,N).
+                    if (last_strip) {
+                        const int ca = V::lo(S[K - 1]), cb = V::hi(S[K - 1]);
+                        lastcol_best_a += g4;
+                        lastcol_best_b += g4;
+                        const bool valid = (i >= 1) && (i <= M);
+                        if (valid && ca >= lastcol_best_a) { lastcol_best_a = ca; lastcol_i_a = i; }
+                        if (NP == 2) { if (valid && cb >= lastcol_best_b) { lastcol_best_b = cb; lastcol_i_b = i; } }
+                    }
+                    // ---- boundary column for the next strip (Vec32 multi-strip) ----------
+                    if (!last_strip && lane == 31 && i >= 1 && i <= M)
+                        bnd_out[i] = make_int2((int)V::raw(S[K - 1]), (int)V::raw(q));
+
+                    // ---- row 0: re-initialise the lane just before its first real row (the steps
+                    // before that computed on padding rows) ---------------------------------------
+                    if (i == 0) GOTOH_ROW0_INIT();
+                    // ---- row M: last-row maximum over this lane's real columns ------------
+                    if (i == M && last_strip) {
+                        const int roff = (NP == 2) ? (M & p.rebase_mask) : M;   // i - base(i)
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const int j = j0 + k + 1;
+                            const int sa = (V::lo(S[k]) >> 2) - (roff + j) * p.gep;
+                            if (j <= Na && sa >= lastrow_best_a) { lastrow_best_a = sa; lastrow_j_a = j; }
+                            if (NP == 2) {
+                                const int sb = (V::hi(S[k]) >> 2) - (roff + j) * p.gep;
+                                if (j <= Nb && sb >= lastrow_best_b) { lastrow_best_b = sb; lastrow_j_b = j; }
+                            }
+                        }
+                    } else if (i == M) {
+                        // earlier strips of a multi-strip task (Vec32): all columns are real
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const int j = j0 + k + 1;
+                            const int sa = (V::lo(S[k]) >> 2) - (M + j) * p.gep;
+                            if (sa >= lastrow_best_a) { lastrow_best_a = sa; lastrow_j_a = j; }
+                        }
+                    }
+                }
+                // one coalesced 512-byte store per warp per STEPS lane-steps
+                p.dir[pa.dir_off + ((int64_t)strip * nblk + tb) * 32 + lane] = dwords;
+            }
+        }
+
+        // ---- K3 epilogue: end-cell choice (gotoh.cpp:418-450) -----------------------------
+        // last row: reduce (score, j) with larger j winning ties
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int os = __shfl_xor_sync(0xffffffffu, lastrow_best_a, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, lastrow_j_a, off);
+            if (os > lastrow_best_a || (os == lastrow_best_a && oj > lastrow_j_a)) { lastrow_best_a = os; lastrow_j_a = oj; }
+            if (NP == 2) {
+                const int os2 = __shfl_xor_sync(0xffffffffu, lastrow_best_b, off);
+                const int oj2 = __shfl_xor_sync(0xffffffffu, lastrow_j_b, off);
+                if (os2 > lastrow_best_b || (os2 == lastrow_best_b && oj2 > lastrow_j_b)) { lastrow_best_b = os2; lastrow_j_b = oj2; }
+            }
+        }
+        // last column: owner lane's tracker; convert from the stored frame of the final step
+        {
+            const int steps_total = nblk * STEPS;
+            const int i_fin = steps_total - lane;          // row index the lane's frame ended in
+            // stored = 4*(S + (i_fin - base + N)*g) with base as of the lane's last rebase
+            int roff_a, roff_b;
+            if (NP == 2) {
+                // rebases happened only while i <= steps_total; the tracker followed every one of them
+                const int R = p.rebase_mask + 1;
+                roff_a = roff_b = i_fin - (i_fin / R) * R;
+            } else {
+                roff_a = roff_b = i_fin;
+            }
+            const int la = (Na - 1) / K - (nstrips - 1) * 32;   // owner lane within the last strip
+            const int lb = (Nb - 1) / K;
+            int best_a = (lastcol_best_a >> 2) - (roff_a + Na) * p.gep;
+            int best_b = (lastcol_best_b >> 2) - (roff_b + Nb) * p.gep;
+            best_a = __shfl_sync(0xffffffffu, best_a, la);
+            const int bi_a = __shfl_sync(0xffffffffu, lastcol_i_a, la);
+            best_b = __shfl_sync(0xffffffffu, best_b, lb & 31);
+            const int bi_b = __shfl_sync(0xffffffffu, lastcol_i_b, lb & 31);
+            if (lane == 0) {
+                // strict '>' : the last row only wins when it is strictly better (gotoh.cpp:429)
+                if (lastrow_best_a > best_a) { p.score[task.pair_a] = lastrow_best_a; p.end_i[task.pair_a] = M; p.end_j[task.pair_a] = lastrow_j_a; }
+                else { p.score[task.pair_a] = best_a; p.end_i[task.pair_a] = bi_a; p.end_j[task.pair_a] = Na; }
+                if (NP == 2 && task.pair_b >= 0) {
+                    if (lastrow_best_b > best_b) { p.score[task.pair_b] = lastrow_best_b; p.end_i[task.pair_b] = M; p.end_j[task.pair_b] = lastrow_j_b; }
+                    else { p.score[task.pair_b] = best_b; p.end_i[task.pair_b] = bi_b; p.end_j[task.pair_b] = Nb; }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K4a  traceback walk: one thread per pair (gotoh.cpp:452-510)
+// ------------------------------------------------------------------------------------
+struct WalkParams {
+    const PairInfo* pairs;
+    int32_t pair_first, pair_count;
+    const uint32_t* dir;        // arena viewed as uint32
+    const int32_t* end_i;
+    const int32_t* end_j;
+    int32_t* score;             // in: S at end cell; out: final score with terminal fix-up
+    uint32_t* ops;              // op scripts, 2 bits per op, 16 per word, in traceback order
+    int32_t* nops;
+    int32_t* i0;
+    int32_t* j0;
+    int32_t* out_len;           // plan order
+    int32_t gip, gep, term;
+};
+
+__global__ void __launch_bounds__(128) k_walk(const WalkParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.pair_count) return;
+    const int pi = p.pair_first + idx;
+    const PairInfo pr = p.pairs[pi];
+    int i = p.end_i[pi], j = p.end_j[pi];
+    const int right = (i == pr.M && j < pr.N) ? (pr.N - j) : (pr.M - i);  // right overhang length
+    uint32_t* ops = p.ops + pr.ops_off;
+    uint32_t cur = 0;
+    int n = 0;
+    int64_t cached_word = -1;
+    uint32_t cached = 0;
+    while (i >= 1 && j >= 1) {
+        const DirAddr a = dir_addr(pr, i, j);
+        if (a.word != cached_word) { cached = p.dir[a.word]; cached_word = a.word; }
+        const uint32_t d = (cached >> a.shift) & 3u;
+        cur |= d << (2 * (n & 15));
+        if ((n & 15) == 15) { ops[n >> 4] = cur; cur = 0; }
+        ++n;
+        if (d == DIR_DIAG) { --i; --j; }
+        else if (d == DIR_UP) { --i; }
+        else { --j; }
+    }
+    if (n & 15) ops[n >> 4] = cur;
+    // left overhang and terminal-gap add-back (gotoh.cpp:491-510): k leftover characters of
+    // exactly one sequence; term==0 ADDS gep per character and gip once.
+    const int k = i > j ? i : j;   // one of them is 0
+    int sc = p.score[pi];
+    if (p.term == 0 && k > 0) sc += k * p.gep + p.gip;
+    p.score[pi] = sc;
+    p.nops[pi] = n;
+    p.i0[pi] = i;
+    p.j0[pi] = j;
+    p.out_len[pi] = k + n + right;
+}
+
+// ------------------------------------------------------------------------------------
+// K4b  string emit: one warp per pair (gotoh.cpp:436-449, 461-476, 493-513)
+// ------------------------------------------------------------------------------------
+struct EmitParams {
+    const PairInfo* pairs;
+    int32_t pair_first, pair_count;
+    const uint8_t* ref_raw;
+    const uint8_t* qry;
+    const uint32_t* ops;
+    const int32_t* nops;
+    const int32_t* i0;
+    const int32_t* j0;
+    const int32_t* end_i;
+    const int32_t* end_j;
+    const int32_t* out_len_plan;   // plan order
+    const int32_t* score_plan;
+    uint8_t* out_ref;
+    uint8_t* out_qry;
+    int32_t* out_len;              // caller order
+    int32_t* out_score;            // caller order
+};
+
+__global__ void __launch_bounds__(128) k_emit(const EmitParams p) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= p.pair_count) return;
+    const int pi = p.pair_first + w;
+    const PairInfo pr = p.pairs[pi];
+    const uint8_t* a = p.ref_raw + pr.ref_pos;
+    const uint8_t* b = p.qry + pr.qry_pos;
+    uint8_t* oa = p.out_ref + pr.out_off;
+    uint8_t* ob = p.out_qry + pr.out_off;
+    const int i0 = p.i0[pi], j0 = p.j0[pi], n = p.nops[pi];
+    const int ei = p.end_i[pi], ej = p.end_j[pi];
+    const uint32_t* ops = p.ops + pr.ops_off;
+    if (lane == 0) { p.out_len[pr.orig] = p.out_len_plan[pi]; p.out_score[pr.orig] = p.score_plan[pi]; }
+
+    // left overhang: the leftover prefix of exactly one sequence against '-'
+    const int lo = i0 > j0 ? i0 : j0;
+    if (i0 > j0) { for (int x = lane; x < lo; x += 32) { oa[x] = a[x]; ob[x] = '-'; } }
+    else { for (int x = lane; x < lo; x += 32) { oa[x] = '-'; ob[x] = b[x]; } }
+
+    // middle: op script reversed; cursors by ballot prefix sums
+    int ia = i0, jb = j0;
+    for (int base = 0; base < n; base += 32) {
+        const int x = base + lane;
+        uint32_t op = 3;
+        if (x < n) { const int f = n - 1 - x; op = (ops[f >> 4] >> (2 * (f & 15))) & 3u; }
+        const bool ca = (x < n) && (op != DIR_LEFT);   // consumes a reference character
+        const bool cb = (x < n) && (op != DIR_UP);     // consumes a query character
+        const unsigned ma = __ballot_sync(0xffffffffu, ca), mb = __ballot_sync(0xffffffffu, cb);
+        const unsigned lt = (1u << lane) - 1u;
+        if (x < n) {
+            oa[lo + x] = ca ? a[ia + __popc(ma & lt)] : (uint8_t)'-';
+            ob[lo + x] = cb ? b[jb + __popc(mb & lt)] : (uint8_t)'-';
+        }
+        ia += __popc(ma);
+        jb += __popc(mb);
+    }
+    // right overhang (gotoh.cpp:434-449)
+    const int ro_base = lo + n;
+    if (ei == pr.M && ej < pr.N) { for (int x = lane; x < pr.N - ej; x += 32) { oa[ro_base + x] = '-'; ob[ro_base + x] = b[ej + x]; } }
+    else { for (int x = lane; x < pr.M - ei; x += 32) { oa[ro_base + x] = a[ei + x]; ob[ro_base + x] = '-'; } }
+}
+
+}  // namespace gotoh

@@ -1,0 +1,91 @@
+"""The exact kernel sources (micall-lite_b200/csrc), compiled for the TEST-ONLY CPU SIMT
+emulator (tests/simt_emu), against the golden vectors and the oracle.  This is how kernel
+logic is checked in the GPU-less container; the -m gpu tests repeat it on the real library."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, run_cases
+
+
+@pytest.fixture(params=["auto", "32"])
+def forced_path(request, monkeypatch):
+    """auto: int16x2 path wherever the range proof allows; 32: everything on the int32 path."""
+    if request.param == "32":
+        monkeypatch.setenv("GOTOH_B200_FORCE_PATH", "32")
+    else:
+        monkeypatch.delenv("GOTOH_B200_FORCE_PATH", raising=False)
+    return request.param
+
+
+def test_emu_appendix_b_and_fuzz(emu_aligner, forced_path):
+    for name in ("appendix_b", "fuzz_small"):
+        n, bad = run_cases(emu_aligner, load_golden(name)["cases"])
+        assert n > 30 and not bad, "%s: %d/%d differ, first %r" % (name, len(bad), n, bad[0])
+
+
+def test_emu_benchmark_shapes(emu_aligner, forced_path):
+    """reads vs HXB2 pol (rebased int16 frames), multi-strip queries, aa windows."""
+    n, bad = run_cases(emu_aligner, load_golden("shapes")["cases"], max_cells=1.2e6)
+    assert n >= 90 and not bad, "%d/%d differ, first %r" % (len(bad), n, bad[0][0])
+
+
+def test_emu_chunked_arena_and_mixed_batch(emu_aligner, oracle_port, monkeypatch):
+    """One batch mixing short and multi-strip queries, several references, forced into many arena
+    chunks; results must come back in caller order."""
+    monkeypatch.setenv("GOTOH_B200_ARENA_MB", "1")
+    rng = random.Random(5)
+    refs = ["".join(rng.choice("ACGT") for _ in range(n)) for n in (700, 90, 333)]
+    queries, ridx = [], []
+    for k in range(60):
+        r = rng.randrange(3)
+        lo = rng.randrange(len(refs[r]) - 40)
+        q = list(refs[r][lo:lo + rng.choice([30, 64, 65, 120, 257, 300])])
+        for _ in range(3):
+            q[rng.randrange(len(q))] = rng.choice("ACGTN")
+        queries.append("".join(q))
+        ridx.append(r)
+    got = emu_aligner.align_batch(refs, queries, 10, 3, 1, 0, ref_idx=ridx)
+    for k in range(60):
+        assert got[k] == oracle_port.align_it(refs[ridx[k]], queries[k], 10, 3, 1), k
+
+
+def test_emu_plan_interface_and_stats(emu_aligner, oracle_port):
+    from gotoh_b200 import packing, workloads
+    ref, qb, qo = workloads.c2_reads_packed(10, seed=3)
+    rb, ro = packing.pack([ref])
+    plan = emu_aligner.plan(rb, ro, np.zeros(10, np.int32), qb, qo, 10, 3, 1, 0)
+    assert plan.cells == int((np.diff(qo) * 3039).sum())
+    assert plan.stat(5) == 10 and plan.stat(6) == 0          # all on the int16x2 path
+    plan.run()
+    plan.run()                                               # re-runnable
+    o_ref, o_qry, o_len, o_score = plan.fetch()
+    a = packing.unpack(o_ref, plan.out_off, o_len)
+    b = packing.unpack(o_qry, plan.out_off, o_len)
+    for k, q in enumerate(workloads.unpacked(qb, qo)):
+        assert (a[k], b[k], int(o_score[k])) == oracle_port.align_it(ref, q, 10, 3, 1)
+    plan.close()
+
+
+def test_emu_input_domain_errors(emu_aligner):
+    from gotoh_b200 import GotohInputError
+    with pytest.raises(GotohInputError):
+        emu_aligner.align_it("  \n", "ACGT", 10, 3, 1)           # empty after trim (gotoh.cpp:555 UB)
+    with pytest.raises(GotohInputError):
+        emu_aligner.align_it("ACGT", "AC\x7fT", 10, 3, 1)        # byte 127 (gotoh.cpp:216-219 OOB)
+    with pytest.raises(GotohInputError):
+        emu_aligner.align_it("ACGT", "ACéT", 10, 3, 1)      # non-ASCII -> bytes >= 128
+    with pytest.raises(GotohInputError):
+        emu_aligner.align_it("A" * 40, "ACGT", 10, 5000, 1)      # -100000 sentinel domain (gotoh.cpp:284)
+    with pytest.raises(ValueError):
+        emu_aligner.align_it("ACGT", "AC\0T", 10, 3, 1)          # "s" rejects embedded NUL
+    assert emu_aligner.align_batch(["ACGT"], [], 10, 3) == []
+
+
+def test_emu_wrapper_semantics(emu_aligner, oracle_port):
+    """trim on both inputs, degap + forced term=0 for align_it_aa_rb (gotoh.cpp:641-642,711-718)."""
+    assert emu_aligner.align_it("  ACGT\n", "\tACT \r\n", 5, 1, 1) == ("ACGT", "AC-T", 9)
+    assert emu_aligner.align_it_aa_rb("K-F-R", "KF--GR", 4, 2) == oracle_port.align_it_aa_rb("K-F-R", "KF--GR", 4, 2)
+    assert emu_aligner.align_it_aa("WWWWKFR", "KFR", 40, 10, 0) == ("WWWWKFR", "----KFR", 104)
