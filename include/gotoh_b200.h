@@ -74,8 +74,8 @@ int32_t gotoh_b200_pairscore_table(int32_t matrix_id, int32_t* out_127x127);
  *     out_ref[out_off[k] .. +out_len[k])  aligned standard   (gotoh.cpp:650 1st string)
  *     out_qry[out_off[k] .. +out_len[k])  aligned seq        (2nd string)
  *     out_score[k]                        alignment score    (3rd value)
- * out_off[k+1]-out_off[k] must be >= M_k+N_k (trimmed lengths); bytes past out_len[k] are
- * left untouched.  No NUL terminators are written.
+ * out_off[k+1]-out_off[k] must be >= M_k+N_k (trimmed lengths); the bytes between
+ * out_len[k] and the pair's stride are set to 0.  No NUL terminators are written.
  *
  * n_refs    number of references (ref_off has n_refs+1 entries)
  * ref_idx   per-pair reference index, or NULL when n_refs == n_pairs and pair k uses ref k

@@ -423,6 +423,10 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     CU(pl->d_ops.alloc((size_t)ops_words));
     CU(pl->d_out_ref.alloc((size_t)pl->out_bytes));
     CU(pl->d_out_qry.alloc((size_t)pl->out_bytes));
+    // bytes between out_len[k] and the pair's stride are never written by k_emit: define them as 0
+    CU(cudaMemsetAsync(pl->d_out_ref.p, 0, (size_t)pl->out_bytes, 0));
+    CU(cudaMemsetAsync(pl->d_out_qry.p, 0, (size_t)pl->out_bytes, 0));
+    CU(cudaDeviceSynchronize());
 
     // ---- arena budget and chunking ----------------------------------------------------------------
     size_t free_b = 0, total_b = 0;

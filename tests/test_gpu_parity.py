@@ -1,0 +1,159 @@
+"""Parity tests proper: the product library (nvcc, sm_100a) on a real B200, through the C ABI,
+against the golden vectors generated from the reference and against the oracle on seeded
+inputs.  Bit-exact: score and both aligned strings.  Nothing here reads /root/reference."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, run_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["auto", "32"])
+def forced_path(request, monkeypatch):
+    if request.param == "32":
+        monkeypatch.setenv("GOTOH_B200_FORCE_PATH", "32")
+    else:
+        monkeypatch.delenv("GOTOH_B200_FORCE_PATH", raising=False)
+    return request.param
+
+
+def test_gpu_golden_vectors(gpu_aligner, forced_path):
+    """Appendix B KATs, 1500 fuzz cases, benchmark shapes incl. 9.6 kb HCV genome pairs."""
+    for name, least in (("appendix_b", 35), ("fuzz_small", 1400), ("shapes", 120)):
+        n, bad = run_cases(gpu_aligner, load_golden(name)["cases"])
+        assert n >= least and not bad, "%s: %d/%d differ, first %r" % (name, len(bad), n, bad[0][0])
+
+
+def test_gpu_drop_in_functions(gpu_aligner, oracle_port):
+    assert gpu_aligner.align_it("ACGT", "ACT", 5, 1, 1) == ("ACGT", "AC-T", 9)
+    assert gpu_aligner.align_it("TACGTA", "ACGT", 5, 1, 0) == ("TACGTA", "-ACGT-", 26)
+    assert gpu_aligner.align_it_aa("WWWWKFR", "KFR", 40, 10, 0) == ("WWWWKFR", "----KFR", 104)
+    assert gpu_aligner.align_it_aa_rb("K-F-R", "KF--GR", 4, 2) == oracle_port.align_it_aa_rb("K-F-R", "KF--GR", 4, 2)
+    import gotoh_b200
+    import gotoh
+    assert gotoh.align_it("  ACGT\n", "\tACT \r\n", 5, 1, 1) == ("ACGT", "AC-T", 9)
+    assert gotoh_b200.align_it_aa("ERM", "ERM", 40, 10, 1) == ("ERM", "ERM", 24)
+
+
+def _check_packed(aligner, oracle, matrix, rb, ro, ridx, qb, qo, gip, gep, term, **kw):
+    got = aligner.align_packed(rb, ro, ridx, qb, qo, gip, gep, term, matrix, **kw)
+    exp = oracle.align_batch(matrix, rb, ro, ridx, qb, qo, gip, gep, term)
+    assert (got[3] == exp[3]).all(), "aligned lengths differ at %r" % np.nonzero(got[3] != exp[3])[0][:5]
+    assert (got[4] == exp[4]).all(), "scores differ at %r" % np.nonzero(got[4] != exp[4])[0][:5]
+    off, ln = exp[2], exp[3]
+    mask = (np.arange(len(got[0]))[None, :] < 0)  # placeholder to keep numpy import used
+    del mask
+    for k in range(len(ln)):
+        s, e = int(off[k]), int(off[k]) + int(ln[k])
+        assert (got[0][s:e] == exp[0][s:e]).all() and (got[1][s:e] == exp[1][s:e]).all(), "pair %d strings differ" % k
+    return got
+
+
+@pytest.mark.parametrize("gip,gep,term", [(10, 3, 1), (10, 10, 0)])
+def test_gpu_c2_reads_vs_oracle(gpu_aligner, oracle_port, gip, gep, term, forced_path):
+    """C2 shape: 251-nt reads vs the 3039-nt HXB2 pol seed; both parameter sweeps of SURVEY 8d."""
+    from gotoh_b200 import packing, workloads
+    ref, qb, qo = workloads.c2_reads_packed(1500, seed=42)
+    rb, ro = packing.pack([ref])
+    _check_packed(gpu_aligner, oracle_port, 0, rb, ro, np.zeros(1500, np.int32), qb, qo, gip, gep, term)
+
+
+@pytest.mark.parametrize("term", [0, 1])
+def test_gpu_c3_amino_vs_oracle(gpu_aligner, oracle_port, term, forced_path):
+    from gotoh_b200 import packing, workloads
+    refs, ridx, qb, qo = workloads.c3_queries_packed(30000, seed=43)
+    rb, ro = packing.pack(refs)
+    _check_packed(gpu_aligner, oracle_port, 1, rb, ro, ridx, qb, qo, 40, 10, term)
+
+
+def test_gpu_c4_long_pairs_vs_oracle(gpu_aligner, oracle_port):
+    """C4 shape: ~9.6 kb x ~9.6 kb, 38 strips of 256 columns per pair, IUPAC codes in the refs."""
+    from gotoh_b200 import packing, workloads
+    refs, ridx, qb, qo = workloads.c4_pairs_packed(12, seed=44)
+    rb, ro = packing.pack(refs)
+    _check_packed(gpu_aligner, oracle_port, 0, rb, ro, ridx, qb, qo, 15, 3, 1)
+
+
+def test_gpu_random_fuzz_batch(gpu_aligner, oracle_port, forced_path):
+    """20k unrelated/related pairs, full byte alphabet of the nt table, all penalty combinations."""
+    from gotoh_b200 import packing
+    rng = random.Random(2026)
+    alpha = "ACGTNRYKMSWBDHVacgtnXx*.-Uu"
+    for gip, gep, term in [(0, 0, 1), (0, 1, 0), (1, 0, 0), (5, 1, 1), (10, 3, 0), (40, 10, 1), (15, 3, 1)]:
+        refs, qs = [], []
+        for _ in range(3000):
+            a = "".join(rng.choice(alpha if rng.random() < 0.3 else "ACGT") for _ in range(rng.randint(1, 300)))
+            if rng.random() < 0.6:
+                lo = rng.randrange(len(a))
+                b = list(a[lo:lo + rng.randint(1, 300)])
+                for _ in range(rng.randint(0, 5)):
+                    b[rng.randrange(len(b))] = rng.choice(alpha)
+                b = "".join(b)
+            else:
+                b = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 300)))
+            refs.append(a)
+            qs.append(b)
+        rb, ro = packing.pack(refs)
+        qb, qo = packing.pack(qs)
+        _check_packed(gpu_aligner, oracle_port, 0, rb, ro, None, qb, qo, gip, gep, term)
+
+
+def test_gpu_paths_agree_and_order_invariance_at_scale(gpu_aligner, monkeypatch):
+    """Size-independent properties on 200k C2 reads (too many for the CPU oracle in a test):
+    the int16x2 and int32 kernels are independent implementations and must agree bit for bit;
+    results do not depend on batch order / warp pairing; degapped outputs reproduce the inputs."""
+    from gotoh_b200 import packing, workloads
+    n = 200000
+    ref, qb, qo = workloads.c2_reads_packed(n, seed=77)
+    rb, ro = packing.pack([ref])
+    ridx = np.zeros(n, np.int32)
+    monkeypatch.delenv("GOTOH_B200_FORCE_PATH", raising=False)
+    a = gpu_aligner.align_packed(rb, ro, ridx, qb, qo, 10, 3, 1, 0)
+    monkeypatch.setenv("GOTOH_B200_FORCE_PATH", "32")
+    b = gpu_aligner.align_packed(rb, ro, ridx, qb, qo, 10, 3, 1, 0)
+    monkeypatch.delenv("GOTOH_B200_FORCE_PATH", raising=False)
+    assert (a[3] == b[3]).all() and (a[4] == b[4]).all()
+    off, ln = a[2], a[3]
+    valid = (np.arange(int(off[-1])) - np.repeat(off[:-1], np.diff(off))) < np.repeat(ln, np.diff(off))
+    assert (a[0][valid] == b[0][valid]).all() and (a[1][valid] == b[1][valid]).all()
+    # reversed batch order -> same per-pair results
+    qs = workloads.unpacked(qb[:qo[2000]], qo[:2001])
+    rq, rqo = packing.pack(qs[::-1])
+    c = gpu_aligner.align_packed(rb, ro, np.zeros(2000, np.int32), rq, rqo, 10, 3, 1, 0)
+    assert (c[4][::-1] == a[4][:2000]).all() and (c[3][::-1] == a[3][:2000]).all()
+    # degapped aligned strings are the (trimmed) inputs; no column is gap/gap
+    for k in range(0, n, 997):
+        s, e = int(off[k]), int(off[k]) + int(ln[k])
+        ar, aq = a[0][s:e], a[1][s:e]
+        assert ar[ar != 45].tobytes().decode() == ref
+        assert (aq[aq != 45] == qb[qo[k]:qo[k + 1]]).all()
+        assert not ((ar == 45) & (aq == 45)).any()
+
+
+def test_gpu_chunked_arena(gpu_aligner, oracle_port, monkeypatch):
+    from gotoh_b200 import packing, workloads
+    monkeypatch.setenv("GOTOH_B200_ARENA_MB", "8")
+    ref, qb, qo = workloads.c2_reads_packed(400, seed=9)
+    rb, ro = packing.pack([ref])
+    _check_packed(gpu_aligner, oracle_port, 0, rb, ro, np.zeros(400, np.int32), qb, qo, 10, 3, 1)
+
+
+def test_gpu_multi_device_sharding_matches_single(gpu_aligner):
+    """device_mask over every visible GPU gives the same bytes as device 0 alone."""
+    from gotoh_b200 import packing, workloads
+    nd = gpu_aligner.device_count()
+    ref, qb, qo = workloads.c2_reads_packed(3000, seed=10)
+    rb, ro = packing.pack([ref])
+    ridx = np.zeros(3000, np.int32)
+    one = gpu_aligner.align_packed(rb, ro, ridx, qb, qo, 10, 3, 1, 0, device_mask=1)
+    allm = gpu_aligner.align_packed(rb, ro, ridx, qb, qo, 10, 3, 1, 0, device_mask=(1 << nd) - 1)
+    assert (one[3] == allm[3]).all() and (one[4] == allm[4]).all()
+    assert (one[0] == allm[0]).all() and (one[1] == allm[1]).all()
+
+
+def test_gpu_int_peak_microbenchmarks_run(gpu_aligner):
+    v = gpu_aligner.int_peak(2)
+    assert v > 100.0   # G thread-instructions/s; a B200 does thousands

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Full-size bench, then the ncu launch list and one --set full capture of the forward kernel.
+set -u
+mkdir -p gpurun_out
+timeout 900 python bench.py > gpurun_out/bench_full.log 2> gpurun_out/bench_full.err; echo "bench_full rc=$?"
+tail -c 2500 gpurun_out/bench_full.log; tail -3 gpurun_out/bench_full.err
+CMD="python bench.py --pairs 60000 --steps 1 --warmup 1 --verify 0 --lite"
+$CMD > gpurun_out/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "ncu launches rc=$?"; tail -2 gpurun_out/plain.log
+$CMD > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_forward -s 1 -c 1 -o gpurun_out/prof_forward $CMD > gpurun_out/ncu_full.log 2>&1
+echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out
