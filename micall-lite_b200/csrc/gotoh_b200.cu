@@ -177,30 +177,30 @@ struct HostPair {
     int32_t orig;
 };
 
-template <class V, int K>
+template <class V, int K, bool MULTI>
 int launch_forward_k(const gotoh_b200_plan* pl, const FwdParams& fp, int ntasks) {
     const size_t per_warp = FwdSmem<V, K>::per_warp(pl->ncls);
     const size_t smem = per_warp * FWD_WARPS;
     if (smem > 200 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
-    CU(cudaFuncSetAttribute(k_forward<V, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_forward<V, K, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid: enough CTAs to fill every SM, tasks are pulled from a counter
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));
     int grid = std::min((ntasks + FWD_WARPS - 1) / FWD_WARPS, pl->sm_count * ctas_per_sm);
-    if (fp.bnd) grid = std::min<long long>(grid, (long long)pl->d_bnd.n / (2 * pl->bnd_stride * FWD_WARPS));
+    if (MULTI) grid = std::min<long long>(grid, (long long)pl->d_bnd.n / (2 * pl->bnd_stride * FWD_WARPS));
     grid = std::max(grid, 1);
-    GOTOH_LAUNCH((k_forward<V, K>), dim3(grid), dim3(FWD_WARPS * 32), smem, pl->stream, fp);
+    GOTOH_LAUNCH((k_forward<V, K, MULTI>), dim3(grid), dim3(FWD_WARPS * 32), smem, pl->stream, fp);
     CU(cudaGetLastError());
     return GOTOH_B200_OK;
 }
 
-template <class V>
+template <class V, bool MULTI>
 int launch_forward(const gotoh_b200_plan* pl, const FwdParams& fp, int K, int ntasks) {
     switch (K) {
-        case 2: return launch_forward_k<V, 2>(pl, fp, ntasks);
-        case 3: return launch_forward_k<V, 3>(pl, fp, ntasks);
-        case 4: return launch_forward_k<V, 4>(pl, fp, ntasks);
-        case 6: return launch_forward_k<V, 6>(pl, fp, ntasks);
-        case 8: return launch_forward_k<V, 8>(pl, fp, ntasks);
+        case 2: return launch_forward_k<V, 2, MULTI>(pl, fp, ntasks);
+        case 3: return launch_forward_k<V, 3, MULTI>(pl, fp, ntasks);
+        case 4: return launch_forward_k<V, 4, MULTI>(pl, fp, ntasks);
+        case 6: return launch_forward_k<V, 6, MULTI>(pl, fp, ntasks);
+        case 8: return launch_forward_k<V, 8, MULTI>(pl, fp, ntasks);
     }
     return fail(GOTOH_B200_EINVAL, "unsupported K=%d", K);
 }
@@ -346,6 +346,8 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     std::sort(wide.begin(), wide.end(), [&](int a, int b) {
         const int ka = pick_K(hp[a].N), kb = pick_K(hp[b].N);
         if (ka != kb) return ka < kb;
+        const bool ma = hp[a].N > 32 * ka, mb = hp[b].N > 32 * kb;   // multi-strip tasks form their own launch
+        if (ma != mb) return mb;
         const long long ca = (long long)hp[a].M * hp[a].N, cb = (long long)hp[b].M * hp[b].N;
         if (ca != cb) return ca > cb;
         return a < b;
@@ -461,14 +463,14 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     for (size_t t = 0; t < pl->tasks.size(); ++t) {
         const TaskMeta& m = tmeta[t];
         if (used + m.arena > budget_u4) { flush(); cur.pair_first = pair_cursor; cur.pair_count = 0; }
-        if (cur.launches.empty() || cur.launches.back().x2 != m.x2 || cur.launches.back().K != m.K) {
+        if (cur.launches.empty() || cur.launches.back().x2 != m.x2 || cur.launches.back().K != m.K ||
+            cur.launches.back().multi_strip != m.multi) {
             Launch L; L.x2 = m.x2; L.K = m.K; L.task_first = (int)t; L.task_count = 0;
-            L.rebase_mask = R - 1; L.multi_strip = 0;
+            L.rebase_mask = R - 1; L.multi_strip = m.multi;
             cur.launches.push_back(L);
         }
         Launch& L = cur.launches.back();
         L.task_count++;
-        L.multi_strip |= m.multi;
         const Task& tk = pl->tasks[t];
         pl->pairs[(size_t)tk.pair_a].dir_off = used;
         if (tk.pair_b >= 0) pl->pairs[(size_t)tk.pair_b].dir_off = used;
@@ -521,8 +523,11 @@ int plan_run(gotoh_b200_plan* pl, float* device_ms, float* forward_ms) {
             fp.bnd = L.multi_strip ? pl->d_bnd.p : nullptr; fp.bnd_stride = pl->bnd_stride;
             fp.score = pl->d_score.p; fp.end_i = pl->d_end_i.p; fp.end_j = pl->d_end_j.p;
             fp.work_counter = pl->d_counter.p + launch_no++;
-            const int rc = L.x2 ? launch_forward<Vec16>(pl, fp, L.K, L.task_count)
-                                : launch_forward<Vec32>(pl, fp, L.K, L.task_count);
+            fp.four = 4u;
+            // multi-strip tasks only exist with K = 8 (pick_K), and only on the int32 path
+            const int rc = L.x2 ? launch_forward<Vec16, false>(pl, fp, L.K, L.task_count)
+                         : (L.multi_strip ? launch_forward_k<Vec32, 8, true>(pl, fp, L.task_count)
+                                          : launch_forward<Vec32, false>(pl, fp, L.K, L.task_count));
             if (rc) return rc;
         }
         if (forward_ms) CU(cudaEventRecord(pl->ev[3], pl->stream));

@@ -1,7 +1,7 @@
 // gotoh_kernels.cuh - sm_100a kernels for MiCall-Lite's Gotoh aligner hot path
 // (reference: /root/reference/micall/alignment/gotoh.cpp:233-527).
 //
-//   k_forward<V,K>  K1/K2/K3: affine-gap forward DP, one warp per task, anti-diagonal
+//   k_forward<V,K,MULTI>  K1/K2/K3: affine-gap forward DP, one warp per task, anti-diagonal
 //                   wavefront across the 32 lanes (lane l owns K query columns and is one
 //                   reference row behind lane l-1), register-resident S/P/Q, shuffle
 //                   hand-off, 2-bit directions packed and stored coalesced, end-cell
@@ -75,7 +75,8 @@ struct FwdParams {
     int32_t ncls;               // number of classes incl. the padding class 0
     int32_t gip, gep;
     int32_t rebase_mask;        // Vec16: R-1 (R power of two); Vec32: unused
-    int32_t smin_m1;            // Vec16: lower bound of any true score, minus 1 (tracking seed)
+    int32_t smin_m1;            // lower bound of any true score, minus 1 (last-column tracking seed)
+    uint32_t four;              // always 4; passed at run time so that acc*four+x compiles to IMAD
     uint4* dir;                 // direction arena
     int2* bnd;                  // Vec32 multi-strip boundary columns: [task_slot][2][bnd_stride]
     int64_t bnd_stride;
@@ -100,6 +101,8 @@ struct Vec32 {
     static __device__ __forceinline__ int lo(T v) { return v; }
     static __device__ __forceinline__ int hi(T v) { return v; }
     static __device__ __forceinline__ unsigned raw(T v) { return (unsigned)v; }
+    // max(a,b) and the predicate a >= b (ties: the new candidate a wins)
+    static __device__ __forceinline__ T bmax(T a, T b, bool* pa, bool* pb) { *pb = false; return __vibmax_s32(a, b, pa); }
 };
 
 struct Vec16 {
@@ -114,6 +117,8 @@ struct Vec16 {
     static __device__ __forceinline__ int lo(T v) { return (int)(short)(v & 0xffffu); }
     static __device__ __forceinline__ int hi(T v) { return (int)(short)(v >> 16); }
     static __device__ __forceinline__ unsigned raw(T v) { return v; }
+    // per-half max and predicates a >= b: one VIMNMX.S16x2 with two predicate outputs (pa: low half)
+    static __device__ __forceinline__ T bmax(T a, T b, bool* pa, bool* pb) { return __vibmax_s16x2(a, b, pb, pa); }
 };
 
 // Location of the 2-bit direction of cell (i,j) (1-based) inside a pair's arena.
@@ -149,48 +154,216 @@ __device__ __forceinline__ DirAddr dir_addr(const PairInfo& p, int i, int j) {
 // ------------------------------------------------------------------------------------
 // K1/K2/K3  forward DP
 // ------------------------------------------------------------------------------------
-#define GOTOH_ROW0_INIT()                                                                          \
-    do {                                                                                           \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) {                                            \
-            /* S(0,j) = 0 and P(0,j) = 0 (gotoh.cpp:267-272) in the frame: 4*j*g (+1 tag for P);  \
-               padding columns clone column N */                                                   \
-            const int ja_ = min(j0 + k + 1, Na), jb_ = min(j0 + k + 1, Nb);                        \
-            S[k] = V::pack(ja_ * g4, jb_ * g4);                                                    \
-            P[k] = V::pack(ja_ * g4 + 1, jb_ * g4 + 1);                                            \
-        }                                                                                          \
-        Sd_in = V::pack(min(j0, Na) * g4, min(j0, Nb) * g4); /* S^(0, j0) */                       \
-        diag0 = V::both(0);                                  /* 4*(i-1)*g at i = 1 */              \
-        /* seed below any reachable score, expressed in the row-0 frame of column N */             \
-        lastcol_best_a = 4 * p.smin_m1 + Na * g4;                                                  \
-        lastcol_best_b = 4 * p.smin_m1 + Nb * g4;                                                  \
-    } while (0)
-
 template <class V, int K>
 struct FwdSmem {
     enum { K4 = (K + 3) / 4 };
-    // profile: [class][K4][lane] of 4 packed entries (int4 for Vec32, uint4 for Vec16)
+    // profile: [class][K4][lane] of 4 packed entries; + a 2x32 int2 ring for multi-strip boundaries
     static __host__ __device__ size_t per_warp(int ncls) { return (size_t)ncls * K4 * 32 * 16 + 2 * 32 * sizeof(int2); }
 };
 
-template <class V, int K>
-__global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
+// State of one warp sweeping one strip (32*K query columns) down the reference.
+// Every member is a register after inlining; all indexing is static.
+template <class V, int K, bool MULTI>
+struct Wave {
     typedef typename V::T T;
     enum { K4 = (K + 3) / 4, STEPS = V::STEPS, NP = V::NPAIR };
+
+    // ---- per-task / per-strip constants --------------------------------------------------
+    int lane, M, Na, Nb, j0, strip, gep, g4, rebase_mask, smin_m1;
+    bool last_strip;
+    unsigned four;                 // == 4 at run time; opaque to ptxas so acc*four+x stays an IMAD (FMA pipe)
+    const uint4* prof_lane;        // prof + lane
+    const uint8_t* cls;            // cls[i-1] = class of reference row i
+    int2* ring;
+    const int2* bnd_in;
+    int2* bnd_out;
+    T c_up, c_sl0, c_q0, c_g4;
+    T Uq[K];
+
+    // ---- lane state ------------------------------------------------------------------------
+    T S[K], P[K];
+    T sendS, sendQ;                // what lane+1 consumes next step: S^(i, j0+K), Q^(i, j0+K)
+    T Sd_in;                       // S^(i-1, j0): diagonal input of column j0+1
+    T diag0;                       // lane 0 / strip 0: "S(i-1,0) = 0" (gotoh.cpp:292) in the stored frame
+    T best;                        // last column: running max in the stored frame of the current row
+    int best_i_a, best_i_b;        //              and its row (largest i wins ties, gotoh.cpp:406-410)
+    int lr_best_a, lr_j_a, lr_best_b, lr_j_b;   // last row (largest j wins ties, gotoh.cpp:399-403)
+    int next_cls;
+    uint4 dwords;
+
+    // S(0,j) = 0 and P(0,j) = 0 (gotoh.cpp:267-272) in the frame: 4*j*g (+1 tag for P); padding
+    // columns (j > N) clone column N so that S[K-1] of the owner lane always reads S^(i,N).
+    __device__ __forceinline__ void row0_init() {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int ja = min(j0 + k + 1, Na), jb = min(j0 + k + 1, Nb);
+            S[k] = V::pack(ja * g4, jb * g4);
+            P[k] = V::pack(ja * g4 + 1, jb * g4 + 1);
+        }
+        Sd_in = V::pack(min(j0, Na) * g4, min(j0, Nb) * g4);   // S^(0, j0)
+        diag0 = V::both(0);                                     // 4*(i-1)*g at i = 1
+        // seed below any reachable score, expressed in the row-0 frame of column N
+        best = V::pack(4 * smin_m1 + Na * g4, 4 * smin_m1 + Nb * g4);
+        best_i_a = best_i_b = 0;
+    }
+
+    // One lane-step: K cells of row i = t - lane.  SLOW adds the rarely needed per-lane checks
+    // (row 0 re-init, int16 rebase, row M capture, i <= M guard); FAST blocks are proven by the
+    // caller to need none of them.
+    template <bool SLOW>
+    __device__ __forceinline__ void step(const int t, const int s) {
+        const int i = t - lane;
+        const int my_cls = next_cls;
+        next_cls = cls[i];                                  // class of row i+1 (padded on both sides)
+
+        // ---- hand-off from the left neighbour (its row i, produced last step) ---------------
+        T Sl = __shfl_up_sync(0xffffffffu, sendS, 1);
+        T Ql = __shfl_up_sync(0xffffffffu, sendQ, 1);
+        T sdiag = Sd_in;
+        if (MULTI && strip > 0) {
+            // boundary column written by the previous strip; staged 32 rows at a time
+            if (((t - 1) & 31) == 0) {
+                __syncwarp();
+                const int row = t + lane;                   // lane 0 is at row t+l at step t+l
+                int2 b = make_int2(0, 0);
+                if (row >= 1 && row <= M) b = bnd_in[row];
+                ring[(((t - 1) >> 5) & 1) * 32 + lane] = b;
+                __syncwarp();
+            }
+            if (lane == 0) {
+                const int2 b = ring[(((t - 1) >> 5) & 1) * 32 + ((t - 1) & 31)];
+                Sl = (T)b.x; Ql = (T)b.y;
+            }
+        } else if (lane == 0) {
+            Sl = c_sl0; Ql = c_q0; sdiag = diag0;           // column 0 (gotoh.cpp:290-293)
+        }
+
+        // ---- int16 range control: rebase every R rows (Vec16 only) --------------------------
+        if (SLOW && NP == 2) {
+            if (i > 0 && (i & rebase_mask) == 0) {
+                const T d = V::both(-(rebase_mask + 1) * g4);
+#pragma unroll
+                for (int k = 0; k < K; ++k) { S[k] = V::add(S[k], d); P[k] = V::add(P[k], d); }
+                sdiag = V::add(sdiag, d);
+                diag0 = V::add(diag0, d);
+                best = V::add(best, d);
+            }
+        }
+        Sd_in = Sl;
+
+        // ---- K cells of row i ------------------------------------------------------------------
+        const uint4* prow = prof_lane + my_cls * (K4 * 32);
+        T sleft = Sl, q = Ql;
+        unsigned accC = 0, accS = 0;
+#pragma unroll
+        for (int kq = 0; kq < K4; ++kq) {
+            const uint4 e4 = prow[kq * 32];
+            const unsigned ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = kq * 4 + kk;
+                if (k < K) {
+                    q = V::addmax(sleft, Uq[k], q);            // Q^ (gotoh.cpp:305-308)
+                    const T pp = V::addmax(S[k], c_up, P[k]);  // P^ (gotoh.cpp:311-314)
+                    const T d = V::add(sdiag, (T)ev[kk]);      // D^ (gotoh.cpp:319)
+                    const T C = V::max3(d, pp, q);             // select + tie-break (gotoh.cpp:362-395)
+                    sdiag = S[k];
+                    P[k] = pp;
+                    S[k] = V::clr(C);
+                    sleft = S[k];
+                    accC = accC * four + V::raw(C);
+                    accS = accS * four + V::raw(S[k]);
+                }
+            }
+        }
+        sendS = S[K - 1];
+        sendQ = q;
+        if (!MULTI || strip == 0) diag0 = V::add(diag0, c_g4);
+
+        // ---- directions: 2K bits per alignment per lane-step -------------------------------------
+        const unsigned dstep = accC - accS;
+        if (NP == 2) {
+            if (s == 0) dwords.x = dstep; else if (s == 1) dwords.y = dstep;
+            else if (s == 2) dwords.z = dstep; else dwords.w = dstep;
+        } else {
+            const unsigned sh = dstep << (16 * (s & 1));
+            if ((s >> 1) == 0) dwords.x = (s & 1) ? (dwords.x | sh) : sh;
+            else if ((s >> 1) == 1) dwords.y = (s & 1) ? (dwords.y | sh) : sh;
+            else if ((s >> 1) == 2) dwords.z = (s & 1) ? (dwords.z | sh) : sh;
+            else dwords.w = (s & 1) ? (dwords.w | sh) : sh;
+        }
+
+        // ---- last column: running max, ties -> larger i (gotoh.cpp:406-410) -----------------------
+        // Tracked in the stored frame of the current row: carrying a score one row down adds 4g.
+        if (!MULTI || last_strip) {
+            best = V::add(best, c_g4);
+            bool pa, pb;
+            const T nb = V::bmax(S[K - 1], best, &pa, &pb);
+            if (!SLOW || i <= M) {
+                best = nb;
+                if (pa) best_i_a = i;
+                if (NP == 2) { if (pb) best_i_b = i; }
+            }
+        }
+        // ---- boundary column for the next strip --------------------------------------------------
+        if (MULTI && !last_strip && lane == 31 && i >= 1 && i <= M)
+            bnd_out[i] = make_int2((int)V::raw(S[K - 1]), (int)V::raw(q));
+
+        if (SLOW) {
+            // row 0: re-initialise the lane just before its first real row
+            if (i == 0) row0_init();
+            // row M: last-row maximum over this lane's real columns
+            if (i == M) {
+                const int roff = (NP == 2) ? (M & rebase_mask) : M;   // i - base(i)
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int j = j0 + k + 1;
+                    const int sa = (V::lo(S[k]) >> 2) - (roff + j) * gep;
+                    if (j <= Na && sa >= lr_best_a) { lr_best_a = sa; lr_j_a = j; }
+                    if (NP == 2) {
+                        const int sb = (V::hi(S[k]) >> 2) - (roff + j) * gep;
+                        if (j <= Nb && sb >= lr_best_b) { lr_best_b = sb; lr_j_b = j; }
+                    }
+                }
+            }
+        }
+    }
+
+    template <bool SLOW>
+    __device__ __forceinline__ void block(const int tb, uint4* dst) {
+#pragma unroll
+        for (int s = 0; s < STEPS; ++s) step<SLOW>(tb * STEPS + s + 1, s);
+        *dst = dwords;   // one coalesced 512-byte store per warp per STEPS lane-steps
+    }
+};
+
+template <class V, int K, bool MULTI>
+__global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
+    typedef typename V::T T;
+    typedef Wave<V, K, MULTI> W;
+    enum { K4 = W::K4, STEPS = V::STEPS, NP = V::NPAIR };
     GOTOH_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* my_smem = smem_raw + (size_t)warp * FwdSmem<V, K>::per_warp(p.ncls);
     uint4* prof = reinterpret_cast<uint4*>(my_smem);
-    int2* ring = reinterpret_cast<int2*>(my_smem + (size_t)p.ncls * K4 * 32 * 16);  // [2][32]
 
-    const int g4 = 4 * p.gep;
+    W w;
+    w.lane = lane;
+    w.gep = p.gep;
+    w.g4 = 4 * p.gep;
+    w.rebase_mask = p.rebase_mask;
+    w.smin_m1 = p.smin_m1;
+    w.four = p.four;
+    w.prof_lane = prof + lane;
+    w.ring = reinterpret_cast<int2*>(my_smem + (size_t)p.ncls * K4 * 32 * 16);  // [2][32]
     const int u4 = -4 * p.gip;
-    const T c_up = V::both(u4 + 1);          // P^ = max(S^up + 4u+1, P^up)
-    const T c_sl0 = V::both(u4);             // column 0 seen by the Q recurrence: s~ = u      (gotoh.cpp:291)
-    const T c_q0 = V::both(2 * u4 + 2);      //                                     q~ = 2u     (gotoh.cpp:293)
-    const T c_g4 = V::both(g4);
+    w.c_up = V::both(u4 + 1);          // P^ = max(S^up + 4u+1, P^up)
+    w.c_sl0 = V::both(u4);             // column 0 seen by the Q recurrence: s~ = u   (gotoh.cpp:291)
+    w.c_q0 = V::both(2 * u4 + 2);      //                                     q~ = 2u  (gotoh.cpp:293)
+    w.c_g4 = V::both(w.g4);
 
     for (;;) {
-        // ---- dynamic task fetch (one atomic per warp) ---------------------------------
+        // ---- dynamic task fetch (one atomic per warp) ---------------------------------------
         unsigned tsk = 0;
         if (lane == 0) tsk = atomicAdd(p.work_counter, 1u);
         tsk = __shfl_sync(0xffffffffu, tsk, 0);
@@ -201,33 +374,32 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
         const int M = pa.M;                       // both halves share the reference
         const int Na = pa.N, Nb = (NP == 2) ? pb.N : pa.N;
         const int Nmax = Na > Nb ? Na : Nb;
-        const int nstrips = (Nmax + 32 * K - 1) / (32 * K);   // Vec16 tasks always have 1
+        const int nstrips = MULTI ? (Nmax + 32 * K - 1) / (32 * K) : 1;
         const int nblk = pa.nblk;
-        const uint8_t* cls = p.ref_cls + pa.ref_pos;          // cls[i-1] = class of row i
         const uint8_t* qa = p.qry + pa.qry_pos;
         const uint8_t* qb = p.qry + pb.qry_pos;
-        int2* bnd0 = p.bnd + ((int64_t)(blockIdx.x * FWD_WARPS + warp) * 2) * p.bnd_stride;  // unused when nstrips == 1
-
-        // running best of the last column (largest i wins ties, gotoh.cpp:406-410) - every
-        // lane tracks its own last register; the owner lane's copy is read in the epilogue
-        int lastcol_best_a = 0, lastcol_i_a = 0, lastcol_best_b = 0, lastcol_i_b = 0;
-        // best of the last row (largest j wins ties, gotoh.cpp:399-403)
-        int lastrow_best_a = -2147483647, lastrow_j_a = 0, lastrow_best_b = -2147483647, lastrow_j_b = 0;
+        int2* bnd0 = MULTI ? p.bnd + ((int64_t)(blockIdx.x * FWD_WARPS + warp) * 2) * p.bnd_stride : nullptr;
+        w.M = M; w.Na = Na; w.Nb = Nb;
+        w.cls = p.ref_cls + pa.ref_pos;
+        w.lr_best_a = w.lr_best_b = -2147483647;
+        w.lr_j_a = w.lr_j_b = 0;
 
         for (int strip = 0; strip < nstrips; ++strip) {
-            const int j0 = (strip * 32 + lane) * K;           // columns j0+1 .. j0+K (1-based)
-            const bool last_strip = (strip == nstrips - 1);
-            int2* bnd_in = bnd0 + (int64_t)((strip + 1) & 1) * p.bnd_stride;
-            int2* bnd_out = bnd0 + (int64_t)(strip & 1) * p.bnd_stride;
+            const int j0 = (strip * 32 + lane) * K;           // this lane owns columns j0+1 .. j0+K
+            w.strip = strip;
+            w.j0 = j0;
+            w.last_strip = (strip == nstrips - 1);
+            if (MULTI) {
+                w.bnd_in = bnd0 + (int64_t)((strip + 1) & 1) * p.bnd_stride;
+                w.bnd_out = bnd0 + (int64_t)(strip & 1) * p.bnd_stride;
+            }
 
-            // ---- query profile for this strip: prof[c][k4][lane].{x,y,z,w} -------------
+            // ---- query profile for this strip: prof[c][k4][lane].{x,y,z,w} ----------------------
             __syncwarp();
-            T Uq[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const int ja = j0 + k;
-                const bool real_a = ja < Na, real_b = ja < Nb;
-                Uq[k] = V::pack(real_a ? u4 + 2 : 3, real_b ? u4 + 2 : 3);
+                const bool real_a = (j0 + k) < Na, real_b = (j0 + k) < Nb;
+                w.Uq[k] = V::pack(real_a ? u4 + 2 : 3, real_b ? u4 + 2 : 3);
             }
             for (int c = 0; c < p.ncls; ++c) {
                 const int32_t* trow = p.table4 + c * 128;
@@ -238,8 +410,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
                     for (int kk = 0; kk < 4; ++kk) {
                         const int ja = j0 + kq * 4 + kk;
                         // padding columns (beyond N) use E = 4u so that they clone column N
-                        const int ea = (ja < Na) ? (int)trow[qa[ja]] : u4;
-                        const int eb = (NP == 2) ? ((ja < Nb) ? (int)trow[qb[ja]] : u4) : 0;
+                        const int ea = (ja < Na) ? trow[qa[ja]] : u4;
+                        const int eb = (NP == 2) ? ((ja < Nb) ? trow[qb[ja]] : u4) : 0;
                         e[kk] = V::raw(V::pack(ea, eb));
                     }
                     prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
@@ -247,192 +419,58 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
             }
             __syncwarp();
 
-            // ---- lane state -----------------------------------------------------------
-            T S[K], P[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) { S[k] = V::both(0); P[k] = V::both(0); }
-            T sendS = V::both(0), sendQ = V::both(0);  // what lane+1 consumes next step
-            T Sd_in = V::both(0);                       // S^(i-1, j0): diagonal input of column j0+1
-            T diag0 = V::both(0);                       // lane 0 / strip 0: "S(i-1,0) = 0" (gotoh.cpp:292) in frame
-            uint4 dwords = make_uint4(0, 0, 0, 0);
-            GOTOH_ROW0_INIT();   // lane 0 starts at row 1 in the very first step
+            w.sendS = V::both(0);
+            w.sendQ = V::both(0);
+            w.dwords = make_uint4(0, 0, 0, 0);
+            w.row0_init();                              // lane 0 starts at row 1 in the very first step
+            w.next_cls = w.cls[-lane];                  // class of row i = 1 - lane (padding when i < 1)
 
-            int next_cls = cls[-lane];                  // class of row i = 1 - lane (padding when i < 1)
-
-            for (int tb = 0; tb < nblk; ++tb) {
-#pragma unroll
-                for (int s = 0; s < STEPS; ++s) {
-                    const int t = tb * STEPS + s + 1;   // 1-based step
-                    const int i = t - lane;             // this lane's row
-                    const int my_cls = next_cls;
-                    next_cls = cls[i];                  // row i+1 (prefetch; padded on both sides)
-
-                    // ---- hand-off from the left neighbour (its row i, produced last step)
-                    T Sl = __shfl_up_sync(0xffffffffu, sendS, 1);
-                    T Ql = __shfl_up_sync(0xffffffffu, sendQ, 1);
-                    if (strip > 0) {
-                        // boundary column written by the previous strip; staged 32 rows at a time
-                        if (((t - 1) & 31) == 0) {
-                            __syncwarp();
-                            const int row = t + lane;   // lane 0 is at row t+l at step t+l
-                            int2 b = make_int2(0, 0);
-                            if (row >= 1 && row <= M) b = bnd_in[row];
-                            ring[(((t - 1) >> 5) & 1) * 32 + lane] = b;
-                            __syncwarp();
-                        }
-                        if (lane == 0) {
-                            const int2 b = ring[(((t - 1) >> 5) & 1) * 32 + ((t - 1) & 31)];
-                            Sl = (T)b.x; Ql = (T)b.y;
-                        }
-                    } else if (lane == 0) {
-                        Sl = c_sl0; Ql = c_q0;
-                    }
-                    T sdiag = Sd_in;
-                    if (strip == 0 && lane == 0) sdiag = diag0;
-
-                    // ---- int16 range control: rebase every R rows (Vec16 only) ---------
-                    if (NP == 2) {
-                        if (i > 0 && (i & p.rebase_mask) == 0) {
-                            const T d = V::both(-(p.rebase_mask + 1) * g4);
-#pragma unroll
-                            for (int k = 0; k < K; ++k) { S[k] = V::add(S[k], d); P[k] = V::add(P[k], d); }
-                            sdiag = V::add(sdiag, d);
-                            diag0 = V::add(diag0, d);
-                            lastcol_best_a += -(p.rebase_mask + 1) * g4;  // tracked in the stored frame
-                            lastcol_best_b += -(p.rebase_mask + 1) * g4;
-                        }
-                    }
-                    Sd_in = Sl;
-
-                    // ---- K cells of row i ------------------------------------------------
-                    const uint4* prow = prof + (my_cls * K4) * 32 + lane;
-                    T sleft = Sl, q = Ql;
-                    unsigned accC = 0, accS = 0;
-#pragma unroll
-                    for (int kq = 0; kq < K4; ++kq) {
-                        const uint4 e4 = prow[kq * 32];
-                        const unsigned ev[4] = {e4.x, e4.y, e4.z, e4.w};
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const int k = kq * 4 + kk;
-                            if (k < K) {
-                                q = V::addmax(sleft, Uq[k], q);            // Q^ (gotoh.cpp:305-308)
-                                const T pp = V::addmax(S[k], c_up, P[k]);  // P^ (gotoh.cpp:311-314)
-                                const T d = V::add(sdiag, (T)ev[kk]);      // D^ (gotoh.cpp:319)
-                                const T C = V::max3(d, pp, q);             // select (gotoh.cpp:362-395)
-                                sdiag = S[k];
-                                P[k] = pp;
-                                S[k] = V::clr(C);
-                                sleft = S[k];
-                                accC = accC * 4u + V::raw(C);
-                                accS = accS * 4u + V::raw(S[k]);
-                            }
-                        }
-                    }
-                    sendS = S[K - 1];
-                    sendQ = q;
-                    diag0 = V::add(diag0, c_g4);
-
-                    // ---- directions: 2K bits per alignment per lane-step -----------------
-                    const unsigned dstep = accC - accS;
-                    if (NP == 2) {
-                        if (s == 0) dwords.x = dstep; else if (s == 1) dwords.y = dstep;
-                        else if (s == 2) dwords.z = dstep; else dwords.w = dstep;
-                    } else {
-                        const unsigned sh = dstep << (16 * (s & 1));
-                        if ((s >> 1) == 0) dwords.x = (s & 1) ? (dwords.x | sh) : sh;
-                        else if ((s >> 1) == 1) dwords.y = (s & 1) ? (dwords.y | sh) : sh;
-                        else if ((s >> 1) == 2) dwords.z = (s & 1) ? (dwords.z | sh) : sh;
-                        else dwords.w = (s & 1) ? (dwords.w | sh) : sh;
-                    }
-
-                    // ---- last column: running max, ties -> larger i (gotoh.cpp:406-410) ---
-                    // tracked in the stored frame of the current row: carrying a score one row
-                    // down adds 4g.  Padding columns clone column N, so S[K-1] of the owner lane
-                    // is S^(i,N).
-                    if (last_strip) {
-                        const int ca = V::lo(S[K - 1]), cb = V::hi(S[K - 1]);
-                        lastcol_best_a += g4;
-                        lastcol_best_b += g4;
-                        const bool valid = (i >= 1) && (i <= M);
-                        if (valid && ca >= lastcol_best_a) { lastcol_best_a = ca; lastcol_i_a = i; }
-                        if (NP == 2) { if (valid && cb >= lastcol_best_b) { lastcol_best_b = cb; lastcol_i_b = i; } }
-                    }
-                    // ---- boundary column for the next strip (Vec32 multi-strip) ----------
-                    if (!last_strip && lane == 31 && i >= 1 && i <= M)
-                        bnd_out[i] = make_int2((int)V::raw(S[K - 1]), (int)V::raw(q));
-
-                    // ---- row 0: re-initialise the lane just before its first real row (the steps
-                    // before that computed on padding rows) ---------------------------------------
-                    if (i == 0) GOTOH_ROW0_INIT();
-                    // ---- row M: last-row maximum over this lane's real columns ------------
-                    if (i == M && last_strip) {
-                        const int roff = (NP == 2) ? (M & p.rebase_mask) : M;   // i - base(i)
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const int j = j0 + k + 1;
-                            const int sa = (V::lo(S[k]) >> 2) - (roff + j) * p.gep;
-                            if (j <= Na && sa >= lastrow_best_a) { lastrow_best_a = sa; lastrow_j_a = j; }
-                            if (NP == 2) {
-                                const int sb = (V::hi(S[k]) >> 2) - (roff + j) * p.gep;
-                                if (j <= Nb && sb >= lastrow_best_b) { lastrow_best_b = sb; lastrow_j_b = j; }
-                            }
-                        }
-                    } else if (i == M) {
-                        // earlier strips of a multi-strip task (Vec32): all columns are real
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const int j = j0 + k + 1;
-                            const int sa = (V::lo(S[k]) >> 2) - (M + j) * p.gep;
-                            if (sa >= lastrow_best_a) { lastrow_best_a = sa; lastrow_j_a = j; }
-                        }
-                    }
+            uint4* dst = p.dir + pa.dir_off + (int64_t)strip * nblk * 32 + lane;
+            for (int tb = 0; tb < nblk; ++tb, dst += 32) {
+                // Which per-lane events can occur in steps t0 .. hi of this block (rows t-31 .. t)?
+                const int t0 = tb * STEPS + 1, hi = t0 + STEPS - 1;
+                bool slow = (t0 <= 31) || (hi >= M);                    // row 0 re-init / row M capture, i <= M
+                if (NP == 2) {
+                    const int m = hi & ~p.rebase_mask;                  // largest multiple of R that is <= hi
+                    slow = slow || (m > 0 && m >= t0 - 31);             // some lane crosses a rebase row
                 }
-                // one coalesced 512-byte store per warp per STEPS lane-steps
-                p.dir[pa.dir_off + ((int64_t)strip * nblk + tb) * 32 + lane] = dwords;
+                if (slow) w.template block<true>(tb, dst);
+                else w.template block<false>(tb, dst);
             }
         }
 
         // ---- K3 epilogue: end-cell choice (gotoh.cpp:418-450) -----------------------------
         // last row: reduce (score, j) with larger j winning ties
+        int lr_best_a = w.lr_best_a, lr_j_a = w.lr_j_a, lr_best_b = w.lr_best_b, lr_j_b = w.lr_j_b;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-            const int os = __shfl_xor_sync(0xffffffffu, lastrow_best_a, off);
-            const int oj = __shfl_xor_sync(0xffffffffu, lastrow_j_a, off);
-            if (os > lastrow_best_a || (os == lastrow_best_a && oj > lastrow_j_a)) { lastrow_best_a = os; lastrow_j_a = oj; }
+            const int os = __shfl_xor_sync(0xffffffffu, lr_best_a, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, lr_j_a, off);
+            if (os > lr_best_a || (os == lr_best_a && oj > lr_j_a)) { lr_best_a = os; lr_j_a = oj; }
             if (NP == 2) {
-                const int os2 = __shfl_xor_sync(0xffffffffu, lastrow_best_b, off);
-                const int oj2 = __shfl_xor_sync(0xffffffffu, lastrow_j_b, off);
-                if (os2 > lastrow_best_b || (os2 == lastrow_best_b && oj2 > lastrow_j_b)) { lastrow_best_b = os2; lastrow_j_b = oj2; }
+                const int os2 = __shfl_xor_sync(0xffffffffu, lr_best_b, off);
+                const int oj2 = __shfl_xor_sync(0xffffffffu, lr_j_b, off);
+                if (os2 > lr_best_b || (os2 == lr_best_b && oj2 > lr_j_b)) { lr_best_b = os2; lr_j_b = oj2; }
             }
         }
-        // last column: owner lane's tracker; convert from the stored frame of the final step
+        // last column: owner lane's tracker, converted from the stored frame of the lane's final row
         {
-            const int steps_total = nblk * STEPS;
-            const int i_fin = steps_total - lane;          // row index the lane's frame ended in
-            // stored = 4*(S + (i_fin - base + N)*g) with base as of the lane's last rebase
-            int roff_a, roff_b;
-            if (NP == 2) {
-                // rebases happened only while i <= steps_total; the tracker followed every one of them
-                const int R = p.rebase_mask + 1;
-                roff_a = roff_b = i_fin - (i_fin / R) * R;
-            } else {
-                roff_a = roff_b = i_fin;
-            }
+            const int i_fin = nblk * STEPS - lane;          // > 0: nblk*STEPS >= M + 31
+            const int roff = (NP == 2) ? (i_fin & p.rebase_mask) : i_fin;   // i_fin - base(i_fin)
             const int la = (Na - 1) / K - (nstrips - 1) * 32;   // owner lane within the last strip
             const int lb = (Nb - 1) / K;
-            int best_a = (lastcol_best_a >> 2) - (roff_a + Na) * p.gep;
-            int best_b = (lastcol_best_b >> 2) - (roff_b + Nb) * p.gep;
+            int best_a = (V::lo(w.best) >> 2) - (roff + Na) * p.gep;
+            int best_b = (V::hi(w.best) >> 2) - (roff + Nb) * p.gep;
             best_a = __shfl_sync(0xffffffffu, best_a, la);
-            const int bi_a = __shfl_sync(0xffffffffu, lastcol_i_a, la);
+            const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a, la);
             best_b = __shfl_sync(0xffffffffu, best_b, lb & 31);
-            const int bi_b = __shfl_sync(0xffffffffu, lastcol_i_b, lb & 31);
+            const int bi_b = __shfl_sync(0xffffffffu, w.best_i_b, lb & 31);
             if (lane == 0) {
                 // strict '>' : the last row only wins when it is strictly better (gotoh.cpp:429)
-                if (lastrow_best_a > best_a) { p.score[task.pair_a] = lastrow_best_a; p.end_i[task.pair_a] = M; p.end_j[task.pair_a] = lastrow_j_a; }
+                if (lr_best_a > best_a) { p.score[task.pair_a] = lr_best_a; p.end_i[task.pair_a] = M; p.end_j[task.pair_a] = lr_j_a; }
                 else { p.score[task.pair_a] = best_a; p.end_i[task.pair_a] = bi_a; p.end_j[task.pair_a] = Na; }
                 if (NP == 2 && task.pair_b >= 0) {
-                    if (lastrow_best_b > best_b) { p.score[task.pair_b] = lastrow_best_b; p.end_i[task.pair_b] = M; p.end_j[task.pair_b] = lastrow_j_b; }
+                    if (lr_best_b > best_b) { p.score[task.pair_b] = lr_best_b; p.end_i[task.pair_b] = M; p.end_j[task.pair_b] = lr_j_b; }
                     else { p.score[task.pair_b] = best_b; p.end_i[task.pair_b] = bi_b; p.end_j[task.pair_b] = Nb; }
                 }
             }

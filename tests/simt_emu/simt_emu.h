@@ -200,6 +200,11 @@ static inline unsigned __vsub2(unsigned a, unsigned b) {
 static inline unsigned __vmaxs2(unsigned a, unsigned b) {
     return simt_pack(max((int)simt_lo(a), (int)simt_lo(b)), max((int)simt_hi(a), (int)simt_hi(b)));
 }
+static inline int __vibmax_s32(int a, int b, bool* p) { *p = a >= b; return a >= b ? a : b; }
+static inline unsigned __vibmax_s16x2(unsigned a, unsigned b, bool* phi, bool* plo) {
+    *plo = simt_lo(a) >= simt_lo(b); *phi = simt_hi(a) >= simt_hi(b);
+    return __vmaxs2(a, b);
+}
 static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vadd2(a, b), c); }
 static inline unsigned __vimax3_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vmaxs2(a, b), c); }
 
