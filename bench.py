@@ -272,17 +272,24 @@ def run_ours(args, rank, world, local_rank):
            (("iadd", 0), ("viaddmnmx", 2), ("viaddmnmx_s16x2", 3), ("vimnmx3", 4), ("vimnmx3_s16x2", 12), ("imad", 5),
             ("lop3", 6), ("alu_plus_imad", 7), ("cell_mix_s16x2", 8), ("cell_mix_s32", 9), ("viadd_16x2", 10))}
     use_x2 = path_x2 >= path_x1
-    issue_peak = mix["cell_mix_s16x2" if use_x2 else "cell_mix_s32"]      # G thread-instr/s of the kernel's own mix
-    instr_per_cell = (sc or {}).get("instr_per_cell_x2" if use_x2 else "instr_per_cell_x1")
-    if instr_per_cell is None:
-        instr_per_cell = 5.2 if use_x2 else 10.4      # hand count, see DESIGN.md 4.2 (replaced by profiles/sass_counts.json)
-    roof_gcups = issue_peak / instr_per_cell
+    tag = "x2" if use_x2 else "x1"
+    alu_rate = mix["viaddmnmx_s16x2" if use_x2 else "viaddmnmx"]     # G thread-instr/s, ALU pipe alone
+    issue_rate = mix["alu_plus_imad"]                                # G thread-instr/s, ALU + FMA pipes together
+    if sc:
+        instr_per_cell, alu_per_cell = sc["instr_per_cell_" + tag], sc["alu_per_cell_" + tag]
+    else:   # hand count of the steady-state block; profiles/sass_counts.json supersedes it
+        instr_per_cell, alu_per_cell = (4.77, 3.09) if use_x2 else (9.47, 6.47)
+    # integer roofline: cells/s at peak INT32 issue / instructions per cell, for the binding constraint
+    roof_alu, roof_issue = alu_rate / alu_per_cell, issue_rate / instr_per_cell
+    roof_gcups = min(roof_alu, roof_issue)
     dir_bytes = 0.25 * cells * (1.03)                 # 2 bits/cell + wavefront fill/drain slots
     roofline = {
-        "bound": "int_alu", "kernel": "k_forward<%s,8>" % ("Vec16" if use_x2 else "Vec32"),
+        "bound": "int_alu", "kernel": "k_forward<%s,8,false>" % ("Vec16" if use_x2 else "Vec32"),
         "achieved": fwd_gcups, "peak": roof_gcups, "unit": "GCUPS", "frac": (fwd_gcups / roof_gcups) if fwd_gcups else None,
-        "peak_def": "measured G thread-instr/s of the kernel's own per-cell instruction mix (%.0f) / SASS instr per cell (%.2f)" % (issue_peak, instr_per_cell),
-        "instr_per_cell": instr_per_cell, "issue_peaks_ginstr_s": mix,
+        "peak_def": "min(measured ALU-pipe rate %.0f G instr/s / %.2f ALU instr per cell, measured ALU+FMA issue rate %.0f / %.2f instr per cell); "
+                    "rates from gotoh_b200_int_peak in this run, counts from cuobjdump (profiles/sass_counts.json)" % (alu_rate, alu_per_cell, issue_rate, instr_per_cell),
+        "instr_per_cell": instr_per_cell, "alu_instr_per_cell": alu_per_cell, "roof_alu_pipe": roof_alu, "roof_issue": roof_issue,
+        "issue_peaks_ginstr_s": mix,
         "avg_launch_ms": fwd_ms_step / max(1, chunks),
         "hbm": {"bound": "hbm", "achieved": dir_bytes / (fwd_ms_step * 1e-3) / 1e9 if fwd_ms_step else None,
                 "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_src": peaks_src,

@@ -28,20 +28,20 @@ __global__ void __launch_bounds__(256) k_peak(int* out, int iters, int b, int c)
     unsigned x[8], y[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { x[j] = threadIdx.x * 7u + j * 13u + (unsigned)b; y[j] = threadIdx.x * 3u + j; }
-    const unsigned ub = (unsigned)b, uc = (unsigned)c;
+    const unsigned ub = (unsigned)b, uc = (unsigned)c, ufour = (unsigned)(c + 9);   // c == -5 at run time
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int rep = 0; rep < 4; ++rep) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (W == W_ADD) x[j] = x[j] + ub;
+                if (W == W_ADD) x[j] = x[j] + x[(j + 1) & 7];
                 else if (W == W_MNMX) { const int m = max((int)x[j], (int)y[j]); y[j] = x[j]; x[j] = (unsigned)m; }
                 else if (W == W_ADDMNMX) x[j] = (unsigned)__viaddmax_s32((int)x[j], b, c);
                 else if (W == W_ADDMNMX16) x[j] = __viaddmax_s16x2(x[j], ub, uc);
                 else if (W == W_MNMX3) x[j] = (unsigned)__vimax3_s32((int)x[j], (int)x[(j + 1) & 7], (int)y[j]);
                 else if (W == W_MNMX3_16) x[j] = __vimax3_s16x2(x[j], x[(j + 1) & 7], y[j]);
                 else if (W == W_IMAD) x[j] = x[j] * ub + uc;
-                else if (W == W_LOP3) x[j] = (x[j] & ub) ^ y[j];
+                else if (W == W_LOP3) x[j] = (x[j] & x[(j + 1) & 7]) ^ y[j];
                 else if (W == W_VADD2) x[j] = __vadd2(x[j], ub);
                 else if (W == W_SHFL) x[j] = __shfl_up_sync(0xffffffffu, x[j], 1);
                 else if (W == W_MIX_ALU_IMAD) { x[j] = (unsigned)__viaddmax_s32((int)x[j], b, c); y[j] = y[j] * ub + uc; }
@@ -53,14 +53,14 @@ __global__ void __launch_bounds__(256) k_peak(int* out, int iters, int b, int c)
                     const unsigned d = __vadd2(x[(j + 2) & 7], ub);
                     const unsigned C = __vimax3_s16x2(d, p, q);
                     x[j] = C & 0xfffcfffcu;
-                    y[j] = (y[j] * 4u + C) - (x[j] * 4u + uc);
+                    y[j] = (y[j] * ufour + C) - (x[j] * ufour + uc);
                 } else if (W == W_CELL32) {
                     const int q = __viaddmax_s32((int)x[j], b, (int)y[j]);
                     const int p = __viaddmax_s32((int)x[(j + 1) & 7], c, q);
                     const int d = (int)x[(j + 2) & 7] + b;
                     const int C = __vimax3_s32(d, p, q);
                     x[j] = (unsigned)(C & ~3);
-                    y[j] = (y[j] * 4u + (unsigned)C) - (x[j] * 4u + uc);
+                    y[j] = (y[j] * ufour + (unsigned)C) - (x[j] * ufour + uc);
                 }
             }
         }
