@@ -1,6 +1,7 @@
 // gotoh_b200.cu - host side of libgotoh_b200.so: C ABI (include/gotoh_b200.h), input
 // validation + trim/degap (gotoh.cpp:529-559), bucketing into warp tasks, HBM layout,
-// kernel launches, multi-GPU static sharding.  The kernels live in gotoh_kernels.cuh.
+// kernel launches, the slab pipeline of the one-shot call, multi-GPU static sharding.
+// The kernels live in gotoh_kernels.cuh.
 //
 // There is no CPU compute path in this file: every entry point that aligns anything
 // requires a CUDA device and fails with GOTOH_B200_ENODEVICE otherwise.
@@ -15,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -68,12 +71,99 @@ extern "C" void* gotoh_b200_host_alloc(int64_t bytes) {
 extern "C" void gotoh_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---------------------------------------------------------------------------------------
-// plan
+// workspaces: grow-only device buffers + pinned staging + one stream
 // ---------------------------------------------------------------------------------------
 namespace {
 
 const int kSupportedK[] = {2, 3, 4, 6, 8};
 const int kMaxK = 8;
+
+template <class T>
+struct DevBuf {            // grow-only device array
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= cap && p) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = std::max<size_t>(count + count / 8, 16);
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) {          // retry without head-room
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, std::max<size_t>(count, 16) * sizeof(T));
+            if (e != cudaSuccess) { p = nullptr; return e; }
+            cap = std::max<size_t>(count, 16);
+            return cudaSuccess;
+        }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T>
+struct PinBuf {            // grow-only page-locked host array (H2D staging)
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= cap && p) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        const size_t want = std::max<size_t>(count + count / 8, 64);
+        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Workspace {
+    int device = 0;
+    bool ready = false;
+    cudaStream_t stream = 0;
+    cudaEvent_t ev[4] = {0, 0, 0, 0};
+    int sm_count = 1;
+    // device
+    DevBuf<uint8_t> d_ref_raw, d_ref_cls, d_qry, d_out_ref, d_out_qry;
+    DevBuf<PairInfo> d_pairs;
+    DevBuf<Task> d_tasks;
+    DevBuf<int32_t> d_table4, d_score, d_end_i, d_end_j, d_nops, d_i0, d_j0, d_len_plan, d_out_len, d_out_score;
+    DevBuf<uint4> d_dir;
+    DevBuf<int2> d_bnd;
+    DevBuf<uint32_t> d_ops, d_counter;
+    // pinned staging
+    PinBuf<uint8_t> h_ref_raw, h_ref_cls, h_qry;
+    PinBuf<PairInfo> h_pairs;
+    PinBuf<Task> h_tasks;
+    PinBuf<int32_t> h_table4;
+
+    int init(int dev) {
+        if (ready) return GOTOH_B200_OK;
+        device = dev;
+        CU(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, dev));
+        sm_count = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&ev[i]));
+        ready = true;
+        return GOTOH_B200_OK;
+    }
+    void release() {
+        if (!ready) return;
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        d_ref_raw.release(); d_ref_cls.release(); d_qry.release(); d_out_ref.release(); d_out_qry.release();
+        d_pairs.release(); d_tasks.release(); d_table4.release(); d_score.release(); d_end_i.release();
+        d_end_j.release(); d_nops.release(); d_i0.release(); d_j0.release(); d_len_plan.release();
+        d_out_len.release(); d_out_score.release(); d_dir.release(); d_bnd.release(); d_ops.release();
+        d_counter.release();
+        h_ref_raw.release(); h_ref_cls.release(); h_qry.release(); h_pairs.release(); h_tasks.release(); h_table4.release();
+        for (int i = 0; i < 4; ++i) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = 0; }
+        if (stream) { cudaStreamDestroy(stream); stream = 0; }
+        ready = false;
+    }
+    ~Workspace() { release(); }
+};
 
 struct Launch {
     int x2;            // 0: Vec32, 1: Vec16
@@ -87,52 +177,26 @@ struct Chunk {
     int pair_first, pair_count;
 };
 
-template <class T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t n = 0;
-    cudaError_t alloc(size_t count) { n = count; return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
-    void release() { if (p) cudaFree(p); p = nullptr; }
-};
-
 }  // namespace
 
 struct gotoh_b200_plan {
-    int device = 0;
-    cudaStream_t stream = 0;
-    cudaEvent_t ev[4] = {0, 0, 0, 0};
+    Workspace* ws = nullptr;
+    bool owns_ws = false;
     int64_t n_pairs = 0;
     int gip = 0, gep = 0, term = 1, matrix = 0;
     int ncls = 1;
     int smin_m1 = 0;
-    int sm_count = 1;
-    std::vector<PairInfo> pairs;
-    std::vector<Task> tasks;
     std::vector<Chunk> chunks;
     int n_launches = 0;
     int64_t out_base = 0, out_bytes = 0;   // caller's out_off range covered by this plan
     int64_t pair_base = 0;                 // first caller pair index
-    // device
-    DevBuf<uint8_t> d_ref_raw, d_ref_cls, d_qry, d_out_ref, d_out_qry;
-    DevBuf<PairInfo> d_pairs;
-    DevBuf<Task> d_tasks;
-    DevBuf<int32_t> d_table4, d_score, d_end_i, d_end_j, d_nops, d_i0, d_j0, d_len_plan, d_out_len, d_out_score;
-    DevBuf<uint4> d_dir;
-    DevBuf<int2> d_bnd;
-    DevBuf<uint32_t> d_ops, d_counter;
     int64_t bnd_stride = 0;
+    int64_t arena_budget_bytes = 0;        // 0: 80 % of free memory
     // stats
     int64_t cells = 0, h2d_bytes = 0, d2h_bytes = 0, arena_bytes = 0, pairs_x2 = 0, pairs_x1 = 0;
 
     ~gotoh_b200_plan() {
-        cudaSetDevice(device);
-        d_ref_raw.release(); d_ref_cls.release(); d_qry.release(); d_out_ref.release(); d_out_qry.release();
-        d_pairs.release(); d_tasks.release(); d_table4.release(); d_score.release(); d_end_i.release();
-        d_end_j.release(); d_nops.release(); d_i0.release(); d_j0.release(); d_len_plan.release();
-        d_out_len.release(); d_out_score.release(); d_dir.release(); d_bnd.release(); d_ops.release();
-        d_counter.release();
-        for (int i = 0; i < 4; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
-        if (stream) cudaStreamDestroy(stream);
+        if (ws && owns_ws) delete ws;
     }
 };
 
@@ -171,24 +235,50 @@ bool fits_int16(int M, int N, int K, int R, int gip, int gep, int minT, int maxT
 }
 
 struct HostPair {
-    int64_t ref;      // reference index
-    int M, N;
-    int64_t qpos;     // position in packed query buffer
+    int32_t ref;      // local reference index
+    int32_t M, N;
     int32_t orig;
+    int64_t qpos;     // position in the packed query buffer
+    int64_t src_lo;   // trimmed span inside the caller's query bytes
 };
+
+struct KeyIdx {
+    uint64_t key;
+    uint32_t idx;
+    bool operator<(const KeyIdx& o) const { return key != o.key ? key < o.key : idx < o.idx; }
+};
+
+// Run fn(lo, hi, tid) over [0, n) on up to `threads` host threads.
+template <class F>
+void parallel_for(int64_t n, int threads, F fn) {
+    threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n));
+    if (threads == 1) { fn((int64_t)0, n, 0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t)
+        th.emplace_back([=]() { fn(n * t / threads, n * (t + 1) / threads, t); });
+    for (auto& x : th) x.join();
+}
+
+int host_threads(int64_t bytes) {
+    if (bytes < (1 << 20)) return 1;
+    const char* e = getenv("GOTOH_B200_HOST_THREADS");
+    int hw = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(hw, 16));
+}
 
 template <class V, int K, bool MULTI>
 int launch_forward_k(const gotoh_b200_plan* pl, const FwdParams& fp, int ntasks) {
+    const Workspace* ws = pl->ws;
     const size_t per_warp = FwdSmem<V, K>::per_warp(pl->ncls);
     const size_t smem = per_warp * FWD_WARPS;
     if (smem > 200 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
     CU(cudaFuncSetAttribute(k_forward<V, K, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid: enough CTAs to fill every SM, tasks are pulled from a counter
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));
-    int grid = std::min((ntasks + FWD_WARPS - 1) / FWD_WARPS, pl->sm_count * ctas_per_sm);
-    if (MULTI) grid = std::min<long long>(grid, (long long)pl->d_bnd.n / (2 * pl->bnd_stride * FWD_WARPS));
+    int grid = std::min((ntasks + FWD_WARPS - 1) / FWD_WARPS, ws->sm_count * ctas_per_sm);
+    if (MULTI) grid = std::min<long long>(grid, (long long)ws->d_bnd.cap / (2 * pl->bnd_stride * FWD_WARPS));
     grid = std::max(grid, 1);
-    GOTOH_LAUNCH((k_forward<V, K, MULTI>), dim3(grid), dim3(FWD_WARPS * 32), smem, pl->stream, fp);
+    GOTOH_LAUNCH((k_forward<V, K, MULTI>), dim3(grid), dim3(FWD_WARPS * 32), smem, ws->stream, fp);
     CU(cudaGetLastError());
     return GOTOH_B200_OK;
 }
@@ -205,97 +295,159 @@ int launch_forward(const gotoh_b200_plan* pl, const FwdParams& fp, int K, int nt
     return fail(GOTOH_B200_EINVAL, "unsupported K=%d", K);
 }
 
+// Validate + trim (+ degap) + pack one contiguous range of caller pairs into the workspace's
+// pinned staging, choose the kernel path per pair, form warp tasks and arena chunks, and
+// enqueue the H2D copies on the workspace stream (no synchronisation).
 int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
                const int32_t* ref_idx, const uint8_t* qry_bytes, const int64_t* qry_off,
                int64_t pair_begin, int64_t pair_end, const int64_t* out_off) {
+    Workspace* ws = pl->ws;
     const int64_t n = pair_end - pair_begin;
     const ScoreTable& tab = score_table(pl->matrix);
     const bool degap = (pl->matrix == GOTOH_B200_AA_RB);
     if (degap) pl->term = 0;   // gotoh.cpp:718
+    if (pl->gip < 0 || pl->gep < 0 || pl->gip > 100000 || pl->gep > 100000)
+        return fail(GOTOH_B200_ESENTINEL, "gap penalties (%d, %d) outside [0, 100000]", pl->gip, pl->gep);
+    CU(cudaSetDevice(ws->device));
+    pl->cells = 0; pl->h2d_bytes = 0; pl->pairs_x1 = pl->pairs_x2 = 0;
 
-    // ---- references used by this shard: trim, degap, validate, classes ------------------
-    std::vector<int64_t> ref_local(n_refs, -1);
+    // ---- references used by this range: trim, degap, validate, classes ------------------
+    std::vector<int32_t> ref_local;
     std::vector<int64_t> used_refs;
-    for (int64_t k = pair_begin; k < pair_end; ++k) {
-        const int64_t r = ref_idx ? ref_idx[k] : k;
-        if (r < 0 || r >= n_refs) return fail(GOTOH_B200_EINVAL, "pair %lld: ref_idx %lld out of range", (long long)k, (long long)r);
-        if (ref_local[r] < 0) { ref_local[r] = (int64_t)used_refs.size(); used_refs.push_back(r); }
+    if (ref_idx) {
+        ref_local.assign((size_t)n_refs, -1);
+        for (int64_t k = pair_begin; k < pair_end; ++k) {
+            const int64_t r = ref_idx[k];
+            if (r < 0 || r >= n_refs) return fail(GOTOH_B200_EINVAL, "pair %lld: ref_idx %lld out of range", (long long)k, (long long)r);
+            if (ref_local[(size_t)r] < 0) { ref_local[(size_t)r] = (int32_t)used_refs.size(); used_refs.push_back(r); }
+        }
+    } else {
+        used_refs.resize((size_t)n);
+        for (int64_t k = 0; k < n; ++k) used_refs[(size_t)k] = pair_begin + k;
     }
-    std::vector<uint8_t> h_ref_raw;
-    std::vector<int64_t> ref_pos(used_refs.size());
-    std::vector<int> ref_len(used_refs.size());
-    bool ref_present[128] = {false}, qry_present[128] = {false};
-    for (size_t u = 0; u < used_refs.size(); ++u) {
+    const size_t nu = used_refs.size();
+    std::vector<int64_t> ref_pos(nu), ref_lo(nu);
+    std::vector<int32_t> ref_len(nu);
+    size_t ref_total = REF_PAD;
+    for (size_t u = 0; u < nu; ++u) {
         const int64_t r = used_refs[u];
-        const uint8_t* s = ref_bytes + ref_off[r];
-        int64_t lo, hi;
         if (ref_off[r + 1] < ref_off[r]) return fail(GOTOH_B200_EINVAL, "ref_off not monotone at %lld", (long long)r);
-        trim_span(s, ref_off[r + 1] - ref_off[r], &lo, &hi);
-        h_ref_raw.insert(h_ref_raw.end(), REF_PAD, 0);
-        ref_pos[u] = (int64_t)h_ref_raw.size();
+        int64_t lo, hi;
+        trim_span(ref_bytes + ref_off[r], ref_off[r + 1] - ref_off[r], &lo, &hi);
+        ref_lo[u] = ref_off[r] + lo;
+        if (hi - lo >= (1 << 24)) return fail(GOTOH_B200_ERANGE, "reference %lld too long", (long long)r);
+        ref_len[u] = (int32_t)(hi - lo);             // upper bound; degap may shrink it below
+        ref_pos[u] = (int64_t)ref_total;
+        ref_total += (size_t)(hi - lo) + REF_PAD;
+    }
+    CU(ws->h_ref_raw.ensure(ref_total));
+    CU(ws->h_ref_cls.ensure(ref_total));
+    uint8_t* h_ref_raw = ws->h_ref_raw.p;
+    memset(h_ref_raw, 0, ref_total);
+    bool ref_present[128] = {false}, qry_present[128] = {false};
+    for (size_t u = 0; u < nu; ++u) {
+        const uint8_t* s = ref_bytes + ref_lo[u];
+        uint8_t* dst = h_ref_raw + ref_pos[u];
+        const int len = ref_len[u];
         int m = 0, dollars = 0;
-        for (int64_t x = lo; x < hi; ++x) {
+        for (int x = 0; x < len; ++x) {
             const uint8_t c = s[x];
             if (degap && c == '-') continue;                       // degap(): gotoh.cpp:529-543
-            if (c < 1 || c > 126) return fail(GOTOH_B200_EDOMAIN, "reference %lld: byte 0x%02x outside 1..126", (long long)r, c);
+            if (c < 1 || c > 126) return fail(GOTOH_B200_EDOMAIN, "reference %lld: byte 0x%02x outside 1..126", (long long)used_refs[u], c);
             dollars = (c == '$') ? dollars + 1 : 0;
             if (dollars >= 3 && pl->matrix == GOTOH_B200_NT)
                 return fail(GOTOH_B200_EDOMAIN, "reference %lld contains \"$$$\": the stop-codon bonus rule "
-                            "(gotoh.cpp:324-344) is not implemented on the device yet", (long long)r);
+                            "(gotoh.cpp:324-344) is not implemented on the device yet", (long long)used_refs[u]);
             ref_present[c] = true;
-            h_ref_raw.push_back(c);
-            ++m;
+            dst[m++] = c;
         }
-        if (m == 0) return fail(GOTOH_B200_EEMPTY, "reference %lld is empty after trim", (long long)r);
-        if ((int64_t)m > (1 << 24)) return fail(GOTOH_B200_ERANGE, "reference %lld too long", (long long)r);
+        if (m == 0) return fail(GOTOH_B200_EEMPTY, "reference %lld is empty after trim", (long long)used_refs[u]);
         ref_len[u] = m;
     }
-    h_ref_raw.insert(h_ref_raw.end(), REF_PAD, 0);
 
-    // ---- queries: trim, degap, validate, pack ---------------------------------------------
-    std::vector<uint8_t> h_qry;
+    // ---- queries, pass 1 (parallel): trim span, validate, length after degap, byte presence ----
     std::vector<HostPair> hp((size_t)n);
-    h_qry.reserve((size_t)(qry_off[pair_end] - qry_off[pair_begin]) + 64);
-    for (int64_t k = pair_begin; k < pair_end; ++k) {
-        const uint8_t* s = qry_bytes + qry_off[k];
-        int64_t lo, hi;
-        if (qry_off[k + 1] < qry_off[k]) return fail(GOTOH_B200_EINVAL, "qry_off not monotone at %lld", (long long)k);
-        trim_span(s, qry_off[k + 1] - qry_off[k], &lo, &hi);
-        HostPair& h = hp[(size_t)(k - pair_begin)];
-        h.qpos = (int64_t)h_qry.size();
-        int nn = 0;
-        for (int64_t x = lo; x < hi; ++x) {
-            const uint8_t c = s[x];
-            if (degap && c == '-') continue;
-            if (c < 1 || c > 126) return fail(GOTOH_B200_EDOMAIN, "query %lld: byte 0x%02x outside 1..126", (long long)k, c);
-            qry_present[c] = true;
-            h_qry.push_back(c);
-            ++nn;
+    const int64_t qbytes_in = qry_off[pair_end] - qry_off[pair_begin];
+    const int nthreads = host_threads(qbytes_in);
+    struct ThreadErr { int code = 0; int64_t pair = -1; int byte = 0; bool present[128] = {false}; int64_t cells = 0; };
+    std::vector<ThreadErr> terr((size_t)nthreads);
+    parallel_for(n, nthreads, [&](int64_t lo_k, int64_t hi_k, int tid) {
+        ThreadErr& te = terr[(size_t)tid];
+        for (int64_t kk = lo_k; kk < hi_k; ++kk) {
+            const int64_t k = pair_begin + kk;
+            HostPair& h = hp[(size_t)kk];
+            if (qry_off[k + 1] < qry_off[k]) { if (!te.code) { te.code = GOTOH_B200_EINVAL; te.pair = k; } return; }
+            const uint8_t* s = qry_bytes + qry_off[k];
+            int64_t lo, hi;
+            trim_span(s, qry_off[k + 1] - qry_off[k], &lo, &hi);
+            if (hi - lo >= (1 << 24)) { if (!te.code) { te.code = GOTOH_B200_ERANGE; te.pair = k; } return; }
+            int nn = 0;
+            unsigned bad = 0;
+            for (int64_t x = lo; x < hi; ++x) {
+                const uint8_t c = s[x];
+                bad |= (unsigned)((uint8_t)(c - 1) > 125);
+                te.present[c & 127] = true;
+                nn += !(degap && c == '-');
+            }
+            if (bad) {
+                if (!te.code) {
+                    te.code = GOTOH_B200_EDOMAIN; te.pair = k;
+                    for (int64_t x = lo; x < hi; ++x) if ((uint8_t)(s[x] - 1) > 125) { te.byte = s[x]; break; }
+                }
+                return;
+            }
+            if (nn == 0) { if (!te.code) { te.code = GOTOH_B200_EEMPTY; te.pair = k; } return; }
+            h.ref = ref_idx ? ref_local[(size_t)ref_idx[k]] : (int32_t)kk;
+            h.M = ref_len[(size_t)h.ref];
+            h.N = nn;
+            h.orig = (int32_t)kk;
+            h.src_lo = qry_off[k] + lo;
+            h.qpos = hi - lo;     // span length for pass 2; replaced by the packed position below
+            // the -100000 sentinel (gotoh.cpp:284-286): outside this bound the reference may read
+            // uninitialised end indices
+            const long long worst = 2LL * pl->gip + ((long long)std::max(h.M, h.N) + 1) * pl->gep;
+            if (worst >= 100000) { if (!te.code) { te.code = GOTOH_B200_ESENTINEL; te.pair = k; } return; }
+            if (out_off[k + 1] - out_off[k] < (int64_t)h.M + h.N || out_off[k + 1] - out_off[k] > 0x7fffffffLL) {
+                if (!te.code) { te.code = GOTOH_B200_ERANGE; te.pair = k; te.byte = -1; }
+                return;
+            }
+            te.cells += (int64_t)h.M * h.N;
         }
-        if (nn == 0) return fail(GOTOH_B200_EEMPTY, "query %lld is empty after trim", (long long)k);
-        if (nn > (1 << 24)) return fail(GOTOH_B200_ERANGE, "query %lld too long", (long long)k);
-        h.ref = ref_local[ref_idx ? ref_idx[k] : k];
-        h.M = ref_len[(size_t)h.ref];
-        h.N = nn;
-        h.orig = (int32_t)(k - pair_begin);
-        // the -100000 sentinel (gotoh.cpp:284-286): outside this bound the reference may read
-        // uninitialised end indices
-        const long long worst = 2LL * pl->gip + ((long long)std::max(h.M, h.N) + 1) * pl->gep;
-        if (worst >= 100000 || pl->gip < 0 || pl->gep < 0 || pl->gip > 100000 || pl->gep > 100000)
-            return fail(GOTOH_B200_ESENTINEL, "pair %lld: 2*gip+(max(M,N)+1)*gep = %lld is outside [0,100000)", (long long)k, worst);
-        if (out_off[k + 1] - out_off[k] < (int64_t)h.M + h.N)
-            return fail(GOTOH_B200_ERANGE, "pair %lld: output stride %lld < M+N = %d", (long long)k,
-                        (long long)(out_off[k + 1] - out_off[k]), h.M + h.N);
-        pl->cells += (int64_t)h.M * h.N;
+    });
+    for (const ThreadErr& te : terr) {
+        if (te.code == GOTOH_B200_EDOMAIN) return fail(te.code, "query %lld: byte 0x%02x outside 1..126", (long long)te.pair, te.byte);
+        if (te.code == GOTOH_B200_EEMPTY) return fail(te.code, "query %lld is empty after trim", (long long)te.pair);
+        if (te.code == GOTOH_B200_ESENTINEL) return fail(te.code, "pair %lld: 2*gip+(max(M,N)+1)*gep >= 100000 (sentinel domain, gotoh.cpp:284)", (long long)te.pair);
+        if (te.code == GOTOH_B200_ERANGE) return fail(te.code, te.byte == -1 ? "pair %lld: output stride smaller than M+N (or >= 2^31)" : "query %lld too long", (long long)te.pair);
+        if (te.code) return fail(te.code, "qry_off not monotone at %lld", (long long)te.pair);
+        for (int c = 0; c < 128; ++c) qry_present[c] |= te.present[c];
+        pl->cells += te.cells;
     }
-    h_qry.insert(h_qry.end(), 64, 0);
+    // ---- pass 2 (parallel): packed positions + copy ------------------------------------------
+    int64_t qtotal = 0;
+    std::vector<int64_t> span((size_t)n);
+    for (int64_t kk = 0; kk < n; ++kk) { span[(size_t)kk] = hp[(size_t)kk].qpos; hp[(size_t)kk].qpos = qtotal; qtotal += hp[(size_t)kk].N; }
+    CU(ws->h_qry.ensure((size_t)qtotal + 64));
+    uint8_t* h_qry = ws->h_qry.p;
+    memset(h_qry + qtotal, 0, 64);
+    parallel_for(n, nthreads, [&](int64_t lo_k, int64_t hi_k, int) {
+        for (int64_t kk = lo_k; kk < hi_k; ++kk) {
+            const HostPair& h = hp[(size_t)kk];
+            const uint8_t* s = qry_bytes + h.src_lo;
+            uint8_t* d = h_qry + h.qpos;
+            if (!degap) memcpy(d, s, (size_t)h.N);
+            else { int m = 0; for (int64_t x = 0; x < span[(size_t)kk]; ++x) if (s[x] != '-') d[m++] = s[x]; }
+        }
+    });
 
     // ---- classes of reference bytes, compact table, score range ----------------------------
     int cls_of[128];
     std::vector<int> rep(1, 0);
     for (int c = 0; c < 128; ++c) { cls_of[c] = 0; if (ref_present[c]) { cls_of[c] = (int)rep.size(); rep.push_back(c); } }
     pl->ncls = (int)rep.size();
-    std::vector<int32_t> h_table4((size_t)pl->ncls * 128, 0);
+    CU(ws->h_table4.ensure((size_t)pl->ncls * 128));
+    int32_t* h_table4 = ws->h_table4.p;
+    memset(h_table4, 0, (size_t)pl->ncls * 128 * sizeof(int32_t));
     int minT = 0, maxT = 0;
     for (int c = 1; c < pl->ncls; ++c)
         for (int b = 1; b < 127; ++b) {
@@ -303,8 +455,8 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
             h_table4[(size_t)c * 128 + b] = 4 * (t + 2 * pl->gep);
             if (qry_present[b]) { minT = std::min(minT, t); maxT = std::max(maxT, t); }
         }
-    std::vector<uint8_t> h_ref_cls(h_ref_raw.size());
-    for (size_t x = 0; x < h_ref_raw.size(); ++x) h_ref_cls[x] = (uint8_t)cls_of[h_ref_raw[x] & 127];
+    uint8_t* h_ref_cls = ws->h_ref_cls.p;
+    for (size_t x = 0; x < ref_total; ++x) h_ref_cls[x] = (uint8_t)cls_of[h_ref_raw[x] & 127];
 
     // ---- choose the path per pair, form warp tasks -------------------------------------------
     // Vec16 (two alignments per warp) needs: single strip (N <= 32*Kmax), same reference for both
@@ -316,56 +468,61 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         smin_all = std::min(smin_all, (long long)std::min(minT, 0) * std::min(h.M, h.N));
     }
     pl->smin_m1 = (int)(smin_all - 2LL * pl->gip - pl->gep - 2);
-    const int force = getenv("GOTOH_B200_FORCE_PATH") ? atoi(getenv("GOTOH_B200_FORCE_PATH")) : 0;  // tests: 32 or 16
-    std::vector<int> elig;   // indices into hp
-    std::vector<int> wide;
+    const int force = getenv("GOTOH_B200_FORCE_PATH") ? atoi(getenv("GOTOH_B200_FORCE_PATH")) : 0;  // tests: 32
+    std::vector<KeyIdx> elig, wide;
+    elig.reserve((size_t)n);
+    int worstM = 0, worstN = 0;   // for picking R: fits_int16 is monotone in min(M,N) and K
     for (size_t x = 0; x < hp.size(); ++x) {
         const HostPair& h = hp[x];
-        const bool ok = h.N <= 32 * kMaxK && force != 32 &&
-                        fits_int16(h.M, h.N, pick_K(h.N), 32, pl->gip, pl->gep, minT, maxT);
-        (ok ? elig : wide).push_back((int)x);
+        const int K = pick_K(h.N);
+        const bool ok = h.N <= 32 * kMaxK && force != 32 && nu < (1u << 26) &&
+                        fits_int16(h.M, h.N, K, 32, pl->gip, pl->gep, minT, maxT);
+        KeyIdx ki;
+        ki.idx = (uint32_t)x;
+        if (ok) {
+            // group by (K, M desc, ref, N desc): partners share the reference and have similar width
+            ki.key = ((uint64_t)K << 59) | ((uint64_t)(0xffffff - h.M) << 35) | ((uint64_t)h.ref << 9) | (uint64_t)(511 - std::min(h.N, 511));
+            elig.push_back(ki);
+            if (std::min(h.M, h.N) > std::min(worstM, worstN)) { worstM = h.M; worstN = h.N; }
+        } else {
+            const bool multi = h.N > 32 * K;   // multi-strip tasks form their own launch
+            const uint64_t cells = (uint64_t)h.M * (uint64_t)h.N;
+            ki.key = ((uint64_t)K << 59) | ((uint64_t)(multi ? 0 : 1) << 58) | ((((uint64_t)1 << 50) - 1 - std::min<uint64_t>(cells, ((uint64_t)1 << 50) - 1)));
+            wide.push_back(ki);
+        }
     }
     int R = 32;
     if (!elig.empty()) {
         for (int cand = 4096; cand >= 32; cand >>= 1) {
             bool all = true;
-            for (int x : elig)
-                if (!fits_int16(hp[x].M, hp[x].N, pick_K(hp[x].N), cand, pl->gip, pl->gep, minT, maxT)) { all = false; break; }
+            for (const KeyIdx& ki : elig) {
+                const HostPair& h = hp[ki.idx];
+                if (!fits_int16(h.M, h.N, pick_K(h.N), cand, pl->gip, pl->gep, minT, maxT)) { all = false; break; }
+            }
             if (all) { R = cand; break; }
         }
     }
-    // order: Vec16 pairs grouped by (K, ref, N) so that partners share the reference and have similar
-    // width; Vec32 pairs by (K, cells desc)
-    std::sort(elig.begin(), elig.end(), [&](int a, int b) {
-        const int ka = pick_K(hp[a].N), kb = pick_K(hp[b].N);
-        if (ka != kb) return ka < kb;
-        if (hp[a].ref != hp[b].ref) return hp[a].M != hp[b].M ? hp[a].M > hp[b].M : hp[a].ref < hp[b].ref;
-        if (hp[a].N != hp[b].N) return hp[a].N > hp[b].N;
-        return a < b;
-    });
-    std::sort(wide.begin(), wide.end(), [&](int a, int b) {
-        const int ka = pick_K(hp[a].N), kb = pick_K(hp[b].N);
-        if (ka != kb) return ka < kb;
-        const bool ma = hp[a].N > 32 * ka, mb = hp[b].N > 32 * kb;   // multi-strip tasks form their own launch
-        if (ma != mb) return mb;
-        const long long ca = (long long)hp[a].M * hp[a].N, cb = (long long)hp[b].M * hp[b].N;
-        if (ca != cb) return ca > cb;
-        return a < b;
-    });
+    std::sort(elig.begin(), elig.end());
+    std::sort(wide.begin(), wide.end());
 
-    pl->pairs.resize((size_t)n);
-    pl->tasks.clear();
+    CU(ws->h_pairs.ensure((size_t)n));
+    CU(ws->h_tasks.ensure((size_t)n));
+    PairInfo* pairs = ws->h_pairs.p;
+    Task* tasks = ws->h_tasks.p;
+    size_t n_tasks = 0;
     struct TaskMeta { int x2, K; int64_t arena; int multi; };
     std::vector<TaskMeta> tmeta;
+    tmeta.reserve((size_t)n);
     int64_t ops_words = 0;
     int next_pair = 0;
-    auto add_pair = [&](int hx, int K, int x2, int half) -> int {
+    auto add_pair = [&](uint32_t hx, int K, int x2, int half) -> int {
         const HostPair& h = hp[hx];
-        PairInfo& pi = pl->pairs[(size_t)next_pair];
+        PairInfo& pi = pairs[next_pair];
         memset(&pi, 0, sizeof(pi));
         pi.ref_pos = ref_pos[(size_t)h.ref];
         pi.qry_pos = h.qpos;
         pi.out_off = out_off[pair_begin + h.orig] - out_off[pair_begin];
+        pi.out_cap = (int32_t)(out_off[pair_begin + h.orig + 1] - out_off[pair_begin + h.orig]);
         pi.M = h.M; pi.N = h.N;
         pi.K = (int16_t)K; pi.x2 = (int8_t)x2; pi.half = (int8_t)half;
         pi.orig = h.orig;
@@ -376,80 +533,69 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         return next_pair++;
     };
     for (size_t x = 0; x < elig.size();) {
-        const int a = elig[x];
+        const uint32_t a = elig[x].idx;
         const int K = pick_K(hp[a].N);
-        int b = -1;
-        if (x + 1 < elig.size() && hp[elig[x + 1]].ref == hp[a].ref && pick_K(hp[elig[x + 1]].N) == K) b = elig[x + 1];
+        int64_t b = -1;
+        if (x + 1 < elig.size() && hp[elig[x + 1].idx].ref == hp[a].ref && pick_K(hp[elig[x + 1].idx].N) == K) b = elig[x + 1].idx;
         Task t;
         t.pair_a = add_pair(a, K, 1, 0);
-        t.pair_b = b >= 0 ? add_pair(b, K, 1, 1) : -1;
+        t.pair_b = b >= 0 ? add_pair((uint32_t)b, K, 1, 1) : -1;
         if (t.pair_a < 0 || (b >= 0 && t.pair_b < 0)) return fail(GOTOH_B200_ERANGE, "op-script arena exceeds 2^31 words; split the batch");
-        pl->tasks.push_back(t);
-        tmeta.push_back({1, K, (int64_t)pl->pairs[(size_t)t.pair_a].nblk * 32, 0});
+        tasks[n_tasks++] = t;
+        tmeta.push_back({1, K, (int64_t)pairs[t.pair_a].nblk * 32, 0});
         pl->pairs_x2 += (b >= 0) ? 2 : 1;
         x += (b >= 0) ? 2 : 1;
     }
-    for (int a : wide) {
+    for (const KeyIdx& ki : wide) {
+        const uint32_t a = ki.idx;
         const int K = pick_K(hp[a].N);
         Task t;
         t.pair_a = add_pair(a, K, 0, 0);
         t.pair_b = -1;
         if (t.pair_a < 0) return fail(GOTOH_B200_ERANGE, "op-script arena exceeds 2^31 words; split the batch");
         const int nstrips = (hp[a].N + 32 * K - 1) / (32 * K);
-        pl->tasks.push_back(t);
-        tmeta.push_back({0, K, (int64_t)nstrips * pl->pairs[(size_t)t.pair_a].nblk * 32, nstrips > 1});
+        tasks[n_tasks++] = t;
+        tmeta.push_back({0, K, (int64_t)nstrips * pairs[t.pair_a].nblk * 32, nstrips > 1});
         pl->pairs_x1 += 1;
     }
-
-    // ---- device setup ---------------------------------------------------------------------------
-    CU(cudaSetDevice(pl->device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, pl->device));
-    pl->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&pl->ev[i]));
 
     pl->out_base = out_off[pair_begin];
     pl->out_bytes = out_off[pair_end] - out_off[pair_begin];
     pl->pair_base = pair_begin;
+    pl->n_pairs = n;
 
-    CU(pl->d_ref_raw.alloc(h_ref_raw.size()));
-    CU(pl->d_ref_cls.alloc(h_ref_cls.size()));
-    CU(pl->d_qry.alloc(h_qry.size()));
-    CU(pl->d_table4.alloc(h_table4.size()));
-    CU(pl->d_pairs.alloc((size_t)n));
-    CU(pl->d_tasks.alloc(pl->tasks.size()));
-    CU(pl->d_score.alloc((size_t)n)); CU(pl->d_end_i.alloc((size_t)n)); CU(pl->d_end_j.alloc((size_t)n));
-    CU(pl->d_nops.alloc((size_t)n)); CU(pl->d_i0.alloc((size_t)n)); CU(pl->d_j0.alloc((size_t)n));
-    CU(pl->d_len_plan.alloc((size_t)n)); CU(pl->d_out_len.alloc((size_t)n)); CU(pl->d_out_score.alloc((size_t)n));
-    CU(pl->d_ops.alloc((size_t)ops_words));
-    CU(pl->d_out_ref.alloc((size_t)pl->out_bytes));
-    CU(pl->d_out_qry.alloc((size_t)pl->out_bytes));
-    // bytes between out_len[k] and the pair's stride are never written by k_emit: define them as 0
-    CU(cudaMemsetAsync(pl->d_out_ref.p, 0, (size_t)pl->out_bytes, 0));
-    CU(cudaMemsetAsync(pl->d_out_qry.p, 0, (size_t)pl->out_bytes, 0));
-    CU(cudaDeviceSynchronize());
+    // ---- device buffers (grow-only, reused across plans on this workspace) ---------------------
+    CU(ws->d_ref_raw.ensure(ref_total));
+    CU(ws->d_ref_cls.ensure(ref_total));
+    CU(ws->d_qry.ensure((size_t)qtotal + 64));
+    CU(ws->d_table4.ensure((size_t)pl->ncls * 128));
+    CU(ws->d_pairs.ensure((size_t)n));
+    CU(ws->d_tasks.ensure(n_tasks));
+    CU(ws->d_score.ensure((size_t)n)); CU(ws->d_end_i.ensure((size_t)n)); CU(ws->d_end_j.ensure((size_t)n));
+    CU(ws->d_nops.ensure((size_t)n)); CU(ws->d_i0.ensure((size_t)n)); CU(ws->d_j0.ensure((size_t)n));
+    CU(ws->d_len_plan.ensure((size_t)n)); CU(ws->d_out_len.ensure((size_t)n)); CU(ws->d_out_score.ensure((size_t)n));
+    CU(ws->d_ops.ensure((size_t)ops_words));
+    CU(ws->d_out_ref.ensure((size_t)pl->out_bytes));
+    CU(ws->d_out_qry.ensure((size_t)pl->out_bytes));
 
     // ---- arena budget and chunking ----------------------------------------------------------------
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    int64_t budget = (int64_t)(free_b * 0.80);
-    if (getenv("GOTOH_B200_ARENA_MB")) budget = (int64_t)atoll(getenv("GOTOH_B200_ARENA_MB")) << 20;  // tests: force chunking
-    int64_t biggest = 0;
-    for (const TaskMeta& m : tmeta) biggest = std::max(biggest, m.arena);
-    // multi-strip boundary columns: two int2 columns of maxM+1 rows per resident warp
+    int64_t biggest = 0, total_arena = 0;
     bool any_multi = false;
-    for (const TaskMeta& m : tmeta) any_multi |= (m.multi != 0);
+    for (const TaskMeta& m : tmeta) { biggest = std::max(biggest, m.arena); total_arena += m.arena; any_multi |= (m.multi != 0); }
     if (any_multi) {
+        // multi-strip boundary columns: two int2 columns of maxM+2 rows per resident warp
         pl->bnd_stride = ((int64_t)maxM + 2 + 15) & ~15LL;
-        const int64_t slots = (int64_t)pl->sm_count * 4 * FWD_WARPS;
-        CU(pl->d_bnd.alloc((size_t)(slots * 2 * pl->bnd_stride)));
-        budget -= slots * 2 * pl->bnd_stride * (int64_t)sizeof(int2);
+        const int64_t slots = (int64_t)ws->sm_count * 4 * FWD_WARPS;
+        CU(ws->d_bnd.ensure((size_t)(slots * 2 * pl->bnd_stride)));
     }
-    const int64_t budget_u4 = std::max<int64_t>(budget / 16, biggest);
-    if (biggest * 16 > (int64_t)free_b)
-        return fail(GOTOH_B200_ENOMEM, "one alignment needs %lld bytes of direction arena, device has %zu free",
-                    (long long)biggest * 16, free_b);
+    int64_t budget = pl->arena_budget_bytes;
+    if (getenv("GOTOH_B200_ARENA_MB")) budget = (int64_t)atoll(getenv("GOTOH_B200_ARENA_MB")) << 20;  // tests: force chunking
+    if (budget <= 0) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        budget = (int64_t)((free_b + ws->d_dir.cap * sizeof(uint4)) * 0.80);
+    }
+    const int64_t budget_u4 = std::max<int64_t>(std::min<int64_t>(budget / 16, total_arena), biggest);
 
     pl->chunks.clear();
     int64_t used = 0, arena_max = 0;
@@ -460,7 +606,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         used = 0;
     };
     int pair_cursor = 0;
-    for (size_t t = 0; t < pl->tasks.size(); ++t) {
+    for (size_t t = 0; t < n_tasks; ++t) {
         const TaskMeta& m = tmeta[t];
         if (used + m.arena > budget_u4) { flush(); cur.pair_first = pair_cursor; cur.pair_count = 0; }
         if (cur.launches.empty() || cur.launches.back().x2 != m.x2 || cur.launches.back().K != m.K ||
@@ -469,11 +615,10 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
             L.rebase_mask = R - 1; L.multi_strip = m.multi;
             cur.launches.push_back(L);
         }
-        Launch& L = cur.launches.back();
-        L.task_count++;
-        const Task& tk = pl->tasks[t];
-        pl->pairs[(size_t)tk.pair_a].dir_off = used;
-        if (tk.pair_b >= 0) pl->pairs[(size_t)tk.pair_b].dir_off = used;
+        cur.launches.back().task_count++;
+        const Task& tk = tasks[t];
+        pairs[tk.pair_a].dir_off = used;
+        if (tk.pair_b >= 0) pairs[tk.pair_b].dir_off = used;
         used += m.arena;
         const int np = tk.pair_b >= 0 ? 2 : 1;
         cur.pair_count += np;
@@ -482,100 +627,110 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     flush();
     pl->n_launches = 0;
     for (const Chunk& c : pl->chunks) pl->n_launches += (int)c.launches.size() + 2;
-    CU(pl->d_dir.alloc((size_t)arena_max));
+    {
+        cudaError_t e = ws->d_dir.ensure((size_t)arena_max);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(GOTOH_B200_ENOMEM, "direction arena of %lld bytes does not fit in device memory", (long long)arena_max * 16);
+        }
+    }
     pl->arena_bytes = arena_max * 16;
-    CU(pl->d_counter.alloc((size_t)std::max(pl->n_launches, 1)));
+    CU(ws->d_counter.ensure((size_t)std::max(pl->n_launches, 1)));
 
-    // ---- H2D ----------------------------------------------------------------------------------------
+    // ---- H2D (async, from pinned staging) ------------------------------------------------------------
     auto h2d = [&](void* d, const void* h, size_t bytes) -> cudaError_t {
         pl->h2d_bytes += (int64_t)bytes;
-        return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, pl->stream);
+        return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ws->stream);
     };
-    CU(h2d(pl->d_ref_raw.p, h_ref_raw.data(), h_ref_raw.size()));
-    CU(h2d(pl->d_ref_cls.p, h_ref_cls.data(), h_ref_cls.size()));
-    CU(h2d(pl->d_qry.p, h_qry.data(), h_qry.size()));
-    CU(h2d(pl->d_table4.p, h_table4.data(), h_table4.size() * sizeof(int32_t)));
-    CU(h2d(pl->d_pairs.p, pl->pairs.data(), pl->pairs.size() * sizeof(PairInfo)));
-    CU(h2d(pl->d_tasks.p, pl->tasks.data(), pl->tasks.size() * sizeof(Task)));
-    CU(cudaStreamSynchronize(pl->stream));   // host staging vectors die at return
+    CU(h2d(ws->d_ref_raw.p, h_ref_raw, ref_total));
+    CU(h2d(ws->d_ref_cls.p, h_ref_cls, ref_total));
+    CU(h2d(ws->d_qry.p, h_qry, (size_t)qtotal + 64));
+    CU(h2d(ws->d_table4.p, h_table4, (size_t)pl->ncls * 128 * sizeof(int32_t)));
+    CU(h2d(ws->d_pairs.p, pairs, (size_t)n * sizeof(PairInfo)));
+    CU(h2d(ws->d_tasks.p, tasks, n_tasks * sizeof(Task)));
     return GOTOH_B200_OK;
 }
 
-int plan_run(gotoh_b200_plan* pl, float* device_ms, float* forward_ms) {
-    CU(cudaSetDevice(pl->device));
-    CU(cudaMemsetAsync(pl->d_counter.p, 0, pl->d_counter.n * sizeof(uint32_t), pl->stream));
-    CU(cudaEventRecord(pl->ev[0], pl->stream));
+// Enqueue forward DP + traceback + emit for every chunk.  With `timed`, CUDA events bracket the
+// whole run (and each chunk's forward launches) and the call synchronises; otherwise it only enqueues.
+int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_ms) {
+    Workspace* ws = pl->ws;
+    CU(cudaSetDevice(ws->device));
+    CU(cudaMemsetAsync(ws->d_counter.p, 0, (size_t)std::max(pl->n_launches, 1) * sizeof(uint32_t), ws->stream));
+    if (timed) CU(cudaEventRecord(ws->ev[0], ws->stream));
     float fwd_total = 0.f;
     int launch_no = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dummy;
     for (size_t ci = 0; ci < pl->chunks.size(); ++ci) {
         const Chunk& c = pl->chunks[ci];
-        if (forward_ms) CU(cudaEventRecord(pl->ev[2], pl->stream));
+        if (timed && forward_ms) CU(cudaEventRecord(ws->ev[2], ws->stream));
         for (const Launch& L : c.launches) {
             FwdParams fp;
             memset(&fp, 0, sizeof(fp));
-            fp.pairs = pl->d_pairs.p; fp.tasks = pl->d_tasks.p;
+            fp.pairs = ws->d_pairs.p; fp.tasks = ws->d_tasks.p;
             fp.task_first = L.task_first; fp.task_count = L.task_count;
-            fp.ref_cls = pl->d_ref_cls.p; fp.qry = pl->d_qry.p; fp.table4 = pl->d_table4.p;
+            fp.ref_cls = ws->d_ref_cls.p; fp.qry = ws->d_qry.p; fp.table4 = ws->d_table4.p;
             fp.ncls = pl->ncls; fp.gip = pl->gip; fp.gep = pl->gep;
             fp.rebase_mask = L.rebase_mask; fp.smin_m1 = pl->smin_m1;
-            fp.dir = pl->d_dir.p;
-            fp.bnd = L.multi_strip ? pl->d_bnd.p : nullptr; fp.bnd_stride = pl->bnd_stride;
-            fp.score = pl->d_score.p; fp.end_i = pl->d_end_i.p; fp.end_j = pl->d_end_j.p;
-            fp.work_counter = pl->d_counter.p + launch_no++;
             fp.four = 4u;
+            fp.dir = ws->d_dir.p;
+            fp.bnd = L.multi_strip ? ws->d_bnd.p : nullptr; fp.bnd_stride = pl->bnd_stride;
+            fp.score = ws->d_score.p; fp.end_i = ws->d_end_i.p; fp.end_j = ws->d_end_j.p;
+            fp.work_counter = ws->d_counter.p + launch_no++;
             // multi-strip tasks only exist with K = 8 (pick_K), and only on the int32 path
             const int rc = L.x2 ? launch_forward<Vec16, false>(pl, fp, L.K, L.task_count)
                          : (L.multi_strip ? launch_forward_k<Vec32, 8, true>(pl, fp, L.task_count)
                                           : launch_forward<Vec32, false>(pl, fp, L.K, L.task_count));
             if (rc) return rc;
         }
-        if (forward_ms) CU(cudaEventRecord(pl->ev[3], pl->stream));
+        if (timed && forward_ms) CU(cudaEventRecord(ws->ev[3], ws->stream));
         WalkParams wp;
         memset(&wp, 0, sizeof(wp));
-        wp.pairs = pl->d_pairs.p; wp.pair_first = c.pair_first; wp.pair_count = c.pair_count;
-        wp.dir = reinterpret_cast<const uint32_t*>(pl->d_dir.p);
-        wp.end_i = pl->d_end_i.p; wp.end_j = pl->d_end_j.p; wp.score = pl->d_score.p;
-        wp.ops = pl->d_ops.p; wp.nops = pl->d_nops.p; wp.i0 = pl->d_i0.p; wp.j0 = pl->d_j0.p;
-        wp.out_len = pl->d_len_plan.p; wp.gip = pl->gip; wp.gep = pl->gep; wp.term = pl->term;
-        GOTOH_LAUNCH(k_walk, dim3((c.pair_count + 127) / 128), dim3(128), 0, pl->stream, wp);
+        wp.pairs = ws->d_pairs.p; wp.pair_first = c.pair_first; wp.pair_count = c.pair_count;
+        wp.dir = reinterpret_cast<const uint32_t*>(ws->d_dir.p);
+        wp.end_i = ws->d_end_i.p; wp.end_j = ws->d_end_j.p; wp.score = ws->d_score.p;
+        wp.ops = ws->d_ops.p; wp.nops = ws->d_nops.p; wp.i0 = ws->d_i0.p; wp.j0 = ws->d_j0.p;
+        wp.out_len = ws->d_len_plan.p; wp.gip = pl->gip; wp.gep = pl->gep; wp.term = pl->term;
+        GOTOH_LAUNCH(k_walk, dim3((c.pair_count + 127) / 128), dim3(128), 0, ws->stream, wp);
         CU(cudaGetLastError());
         EmitParams ep;
         memset(&ep, 0, sizeof(ep));
-        ep.pairs = pl->d_pairs.p; ep.pair_first = c.pair_first; ep.pair_count = c.pair_count;
-        ep.ref_raw = pl->d_ref_raw.p; ep.qry = pl->d_qry.p; ep.ops = pl->d_ops.p; ep.nops = pl->d_nops.p;
-        ep.i0 = pl->d_i0.p; ep.j0 = pl->d_j0.p; ep.end_i = pl->d_end_i.p; ep.end_j = pl->d_end_j.p;
-        ep.out_len_plan = pl->d_len_plan.p; ep.score_plan = pl->d_score.p;
-        ep.out_ref = pl->d_out_ref.p; ep.out_qry = pl->d_out_qry.p;
-        ep.out_len = pl->d_out_len.p; ep.out_score = pl->d_out_score.p;
-        GOTOH_LAUNCH(k_emit, dim3((c.pair_count + 3) / 4), dim3(128), 0, pl->stream, ep);
+        ep.pairs = ws->d_pairs.p; ep.pair_first = c.pair_first; ep.pair_count = c.pair_count;
+        ep.ref_raw = ws->d_ref_raw.p; ep.qry = ws->d_qry.p; ep.ops = ws->d_ops.p; ep.nops = ws->d_nops.p;
+        ep.i0 = ws->d_i0.p; ep.j0 = ws->d_j0.p; ep.end_i = ws->d_end_i.p; ep.end_j = ws->d_end_j.p;
+        ep.out_len_plan = ws->d_len_plan.p; ep.score_plan = ws->d_score.p;
+        ep.out_ref = ws->d_out_ref.p; ep.out_qry = ws->d_out_qry.p;
+        ep.out_len = ws->d_out_len.p; ep.out_score = ws->d_out_score.p;
+        GOTOH_LAUNCH(k_emit, dim3((c.pair_count + 3) / 4), dim3(128), 0, ws->stream, ep);
         CU(cudaGetLastError());
-        if (forward_ms) {
-            CU(cudaEventSynchronize(pl->ev[3]));
+        if (timed && forward_ms) {
+            CU(cudaEventSynchronize(ws->ev[3]));
             float ms = 0.f;
-            CU(cudaEventElapsedTime(&ms, pl->ev[2], pl->ev[3]));
+            CU(cudaEventElapsedTime(&ms, ws->ev[2], ws->ev[3]));
             fwd_total += ms;
         }
     }
-    CU(cudaEventRecord(pl->ev[1], pl->stream));
-    CU(cudaEventSynchronize(pl->ev[1]));
-    if (device_ms) CU(cudaEventElapsedTime(device_ms, pl->ev[0], pl->ev[1]));
-    if (forward_ms) *forward_ms = fwd_total;
+    if (timed) {
+        CU(cudaEventRecord(ws->ev[1], ws->stream));
+        CU(cudaEventSynchronize(ws->ev[1]));
+        if (device_ms) CU(cudaEventElapsedTime(device_ms, ws->ev[0], ws->ev[1]));
+        if (forward_ms) *forward_ms = fwd_total;
+    }
     return GOTOH_B200_OK;
 }
 
+// Enqueue the D2H copies of the plan's results into the caller's buffers (no synchronisation).
 int plan_fetch(gotoh_b200_plan* pl, uint8_t* out_ref, uint8_t* out_qry, int32_t* out_len, int32_t* out_score) {
-    CU(cudaSetDevice(pl->device));
+    Workspace* ws = pl->ws;
+    CU(cudaSetDevice(ws->device));
     pl->d2h_bytes = 0;
     auto d2h = [&](void* h, const void* d, size_t bytes) -> cudaError_t {
         pl->d2h_bytes += (int64_t)bytes;
-        return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, pl->stream);
+        return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ws->stream);
     };
-    CU(d2h(out_ref + pl->out_base, pl->d_out_ref.p, (size_t)pl->out_bytes));
-    CU(d2h(out_qry + pl->out_base, pl->d_out_qry.p, (size_t)pl->out_bytes));
-    CU(d2h(out_len + pl->pair_base, pl->d_out_len.p, (size_t)pl->n_pairs * sizeof(int32_t)));
-    CU(d2h(out_score + pl->pair_base, pl->d_out_score.p, (size_t)pl->n_pairs * sizeof(int32_t)));
-    CU(cudaStreamSynchronize(pl->stream));
+    CU(d2h(out_ref + pl->out_base, ws->d_out_ref.p, (size_t)pl->out_bytes));
+    CU(d2h(out_qry + pl->out_base, ws->d_out_qry.p, (size_t)pl->out_bytes));
+    CU(d2h(out_len + pl->pair_base, ws->d_out_len.p, (size_t)pl->n_pairs * sizeof(int32_t)));
+    CU(d2h(out_score + pl->pair_base, ws->d_out_score.p, (size_t)pl->n_pairs * sizeof(int32_t)));
     return GOTOH_B200_OK;
 }
 
@@ -588,6 +743,78 @@ int check_common(const void* ref_bytes, const int64_t* ref_off, int64_t n_refs, 
     if (!ref_idx && n_refs != n_pairs) return fail(GOTOH_B200_EINVAL, "ref_idx is NULL but n_refs != n_pairs");
     if (matrix_id < 0 || matrix_id > 2) return fail(GOTOH_B200_EINVAL, "matrix_id %d not in {0,1,2}", matrix_id);
     return GOTOH_B200_OK;
+}
+
+// ---- cached per-device contexts for the one-shot call: two workspaces = two slabs in flight ----
+struct DeviceCtx {
+    std::mutex mu;
+    Workspace ws[2];
+};
+std::mutex g_ctx_mu;
+DeviceCtx* g_ctx[64] = {nullptr};
+
+DeviceCtx* ctx_for(int dev) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!g_ctx[dev]) g_ctx[dev] = new (std::nothrow) DeviceCtx();
+    return g_ctx[dev];
+}
+
+// One device's share [lo, hi) of a one-shot call: cut into slabs of bounded arena size, each slab is a
+// self-contained plan on one of two workspaces (streams), so host packing of slab s+1 and the D2H of
+// slab s overlap the kernels of the slab in between.
+int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
+                     const int32_t* ref_idx, const uint8_t* qry_bytes, const int64_t* qry_off,
+                     int64_t lo, int64_t hi, int32_t gip, int32_t gep, int32_t term, int32_t matrix_id,
+                     uint8_t* out_ref, uint8_t* out_qry, const int64_t* out_off, int32_t* out_len, int32_t* out_score) {
+    DeviceCtx* ctx = ctx_for(dev);
+    if (!ctx) return fail(GOTOH_B200_ENOMEM, "out of host memory");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (int w = 0; w < 2; ++w) { const int rc = ctx->ws[w].init(dev); if (rc) return rc; }
+    CU(cudaSetDevice(dev));
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const int64_t cached = (int64_t)(ctx->ws[0].d_dir.cap + ctx->ws[1].d_dir.cap) * 16;
+    int64_t slab_budget = std::min<int64_t>(((int64_t)free_b + cached) / 5, (int64_t)24 << 30);
+    slab_budget = std::max<int64_t>(slab_budget, (int64_t)256 << 20);
+    if (getenv("GOTOH_B200_SLAB_MB")) slab_budget = (int64_t)atoll(getenv("GOTOH_B200_SLAB_MB")) << 20;   // tests
+    gotoh_b200_plan plans[2];
+    for (int w = 0; w < 2; ++w) {
+        plans[w].ws = &ctx->ws[w];
+        plans[w].gip = gip; plans[w].gep = gep; plans[w].term = term ? 1 : 0; plans[w].matrix = matrix_id;
+        plans[w].arena_budget_bytes = slab_budget;
+    }
+    int rc = GOTOH_B200_OK;
+    int slab = 0;
+    for (int64_t k = lo; k < hi && !rc;) {
+        // slab = as many consecutive pairs as fit the arena estimate ((M+40)*64 B per strip per pair)
+        int64_t est = 0, e = k;
+        while (e < hi) {
+            const int64_t r = ref_idx ? ref_idx[e] : e;
+            const int64_t m = (r >= 0 && r < n_refs) ? ref_off[r + 1] - ref_off[r] : 0;
+            const int64_t nq = qry_off[e + 1] - qry_off[e];
+            const int64_t need = (std::max<int64_t>(nq, 1) + 255) / 256 * (m + 40) * 64;
+            if (e > k && (est + need > slab_budget || e - k >= (1 << 20))) break;
+            est += need;
+            ++e;
+        }
+        gotoh_b200_plan* pl = &plans[slab & 1];
+        // the workspace's previous slab (two slabs ago) must have drained before its staging is reused
+        if (cudaStreamSynchronize(pl->ws->stream) != cudaSuccess) { rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed"); break; }
+        try {
+            rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, k, e, out_off);
+        } catch (const std::bad_alloc&) {
+            rc = fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
+        }
+        if (!rc) rc = plan_run(pl, false, nullptr, nullptr);
+        if (!rc) rc = plan_fetch(pl, out_ref, out_qry, out_len, out_score);
+        k = e;
+        ++slab;
+    }
+    for (int w = 0; w < 2; ++w) {
+        const cudaError_t e = cudaStreamSynchronize(ctx->ws[w].stream);
+        if (e != cudaSuccess && !rc) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 }  // namespace
@@ -605,15 +832,20 @@ extern "C" int32_t gotoh_b200_plan_create(int32_t device, const uint8_t* ref_byt
     if (ndev <= 0) return fail(GOTOH_B200_ENODEVICE, "no CUDA device is visible; libgotoh_b200 has no CPU path");
     if (device < 0 || device >= ndev) return fail(GOTOH_B200_ENODEVICE, "device %d not present (%d visible)", device, ndev);
     gotoh_b200_plan* pl = new (std::nothrow) gotoh_b200_plan();
-    if (!pl) return fail(GOTOH_B200_ENOMEM, "out of host memory");
-    pl->device = device;
-    pl->n_pairs = n_pairs;
+    Workspace* ws = new (std::nothrow) Workspace();
+    if (!pl || !ws) { delete pl; delete ws; return fail(GOTOH_B200_ENOMEM, "out of host memory"); }
+    pl->ws = ws;
+    pl->owns_ws = true;
     pl->gip = gip; pl->gep = gep; pl->term = use_terminal ? 1 : 0; pl->matrix = matrix_id;
-    try {
-        rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, 0, n_pairs, out_off);
-    } catch (const std::bad_alloc&) {
-        rc = fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
+    rc = ws->init(device);
+    if (!rc) {
+        try {
+            rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, 0, n_pairs, out_off);
+        } catch (const std::bad_alloc&) {
+            rc = fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
+        }
     }
+    if (!rc && cudaStreamSynchronize(ws->stream) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "H2D copy failed");
     if (rc) { delete pl; return rc; }
     *plan_out = pl;
     return GOTOH_B200_OK;
@@ -621,13 +853,16 @@ extern "C" int32_t gotoh_b200_plan_create(int32_t device, const uint8_t* ref_byt
 
 extern "C" int32_t gotoh_b200_plan_run(gotoh_b200_plan* plan, float* device_ms, float* forward_ms) {
     if (!plan) return fail(GOTOH_B200_EINVAL, "plan is NULL");
-    return plan_run(plan, device_ms, forward_ms);
+    return plan_run(plan, true, device_ms, forward_ms);
 }
 
 extern "C" int32_t gotoh_b200_plan_fetch(gotoh_b200_plan* plan, uint8_t* out_ref, uint8_t* out_qry,
                                          int32_t* out_len, int32_t* out_score) {
     if (!plan || !out_ref || !out_qry || !out_len || !out_score) return fail(GOTOH_B200_EINVAL, "NULL argument");
-    return plan_fetch(plan, out_ref, out_qry, out_len, out_score);
+    const int rc = plan_fetch(plan, out_ref, out_qry, out_len, out_score);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(plan->ws->stream));
+    return GOTOH_B200_OK;
 }
 
 extern "C" void gotoh_b200_plan_destroy(gotoh_b200_plan* plan) { delete plan; }
@@ -645,6 +880,16 @@ extern "C" int64_t gotoh_b200_plan_stat(const gotoh_b200_plan* pl, int32_t what)
         case 7: return (int64_t)pl->chunks.size();
     }
     return -1;
+}
+
+extern "C" void gotoh_b200_release_cache(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (int d = 0; d < 64; ++d)
+        if (g_ctx[d]) {
+            std::lock_guard<std::mutex> lk2(g_ctx[d]->mu);
+            g_ctx[d]->ws[0].release();
+            g_ctx[d]->ws[1].release();
+        }
 }
 
 // One-shot form.  Shards contiguous pair ranges of (nearly) equal cell count across the
@@ -671,7 +916,8 @@ extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_
     // contiguous split balanced by an O(n) cell estimate (untrimmed lengths)
     const int D = (int)std::min<int64_t>((int64_t)devs.size(), n_pairs);
     std::vector<int64_t> cut(D + 1, 0);
-    {
+    cut[D] = n_pairs;
+    if (D > 1) {
         std::vector<double> pre((size_t)n_pairs + 1, 0.0);
         for (int64_t k = 0; k < n_pairs; ++k) {
             const int64_t r = ref_idx ? ref_idx[k] : k;
@@ -684,27 +930,13 @@ extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_
             cut[d] = std::max(cut[d], cut[d - 1] + 1);
             cut[d] = std::min<int64_t>(cut[d], n_pairs - (D - d));
         }
-        cut[D] = n_pairs;
     }
     std::vector<int> rcs(D, 0);
     std::vector<std::string> msgs(D);
     auto work = [&](int d) {
-        gotoh_b200_plan* pl = new (std::nothrow) gotoh_b200_plan();
-        if (!pl) { rcs[d] = GOTOH_B200_ENOMEM; msgs[d] = "out of host memory"; return; }
-        pl->device = devs[d];
-        pl->n_pairs = cut[d + 1] - cut[d];
-        pl->gip = gip; pl->gep = gep; pl->term = use_terminal ? 1 : 0; pl->matrix = matrix_id;
-        int r;
-        try {
-            r = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, cut[d], cut[d + 1], out_off);
-            if (!r) r = plan_run(pl, nullptr, nullptr);
-            if (!r) r = plan_fetch(pl, out_ref, out_qry, out_len, out_score);
-        } catch (const std::bad_alloc&) {
-            r = fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
-        }
-        rcs[d] = r;
-        if (r) msgs[d] = g_err;
-        delete pl;
+        rcs[d] = run_device_range(devs[d], ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, cut[d], cut[d + 1],
+                                  gip, gep, use_terminal, matrix_id, out_ref, out_qry, out_off, out_len, out_score);
+        if (rcs[d]) msgs[d] = g_err;
     };
     if (D == 1) work(0);
     else {

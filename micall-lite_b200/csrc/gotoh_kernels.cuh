@@ -56,8 +56,9 @@ struct PairInfo {
     int16_t K;         // query columns per lane
     int8_t x2;         // 1: Vec16 arena (32 dir bits per lane-step, two alignments)
     int8_t half;       // which half of the Vec16 word belongs to this pair
-    int32_t orig;      // caller's pair index
-    int32_t pad0, pad1;
+    int32_t orig;      // caller's pair index (relative to the plan's first pair)
+    int32_t out_cap;   // caller's output stride for this pair (>= M+N); the tail past out_len is zeroed
+    int32_t pad1;
 };
 
 struct Task {          // one warp's work item
@@ -595,6 +596,8 @@ __global__ void __launch_bounds__(128) k_emit(const EmitParams p) {
     const int ro_base = lo + n;
     if (ei == pr.M && ej < pr.N) { for (int x = lane; x < pr.N - ej; x += 32) { oa[ro_base + x] = '-'; ob[ro_base + x] = b[ej + x]; } }
     else { for (int x = lane; x < pr.M - ei; x += 32) { oa[ro_base + x] = a[ei + x]; ob[ro_base + x] = '-'; } }
+    // bytes between out_len and the caller's stride are defined as 0
+    for (int x = p.out_len_plan[pi] + lane; x < pr.out_cap; x += 32) { oa[x] = 0; ob[x] = 0; }
 }
 
 }  // namespace gotoh

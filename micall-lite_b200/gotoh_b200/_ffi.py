@@ -20,6 +20,7 @@ SYMBOLS = (
     "gotoh_b200_pairscore_table", "gotoh_b200_align_batch", "gotoh_b200_plan_create",
     "gotoh_b200_plan_run", "gotoh_b200_plan_fetch", "gotoh_b200_plan_destroy",
     "gotoh_b200_plan_stat", "gotoh_b200_host_alloc", "gotoh_b200_host_free", "gotoh_b200_int_peak",
+    "gotoh_b200_release_cache",
 )
 
 
@@ -67,6 +68,8 @@ class Library:
         lib.gotoh_b200_host_alloc.argtypes = [_i64]
         lib.gotoh_b200_host_free.restype = None
         lib.gotoh_b200_host_free.argtypes = [_vp]
+        lib.gotoh_b200_release_cache.restype = None
+        lib.gotoh_b200_release_cache.argtypes = []
         lib.gotoh_b200_int_peak.restype = _i32
         lib.gotoh_b200_int_peak.argtypes = [_i32, _i32, ctypes.POINTER(ctypes.c_double)]
         self.lib = lib

@@ -52,6 +52,20 @@ def test_emu_chunked_arena_and_mixed_batch(emu_aligner, oracle_port, monkeypatch
         assert got[k] == oracle_port.align_it(refs[ridx[k]], queries[k], 10, 3, 1), k
 
 
+def test_emu_slab_pipeline_many_slabs(emu_aligner, oracle_port, monkeypatch):
+    """The one-shot call cuts the batch into slabs that ping-pong between two workspaces; force
+    one slab per handful of pairs and check order, contents and the zeroed stride tails."""
+    from gotoh_b200 import packing, workloads
+    monkeypatch.setenv("GOTOH_B200_SLAB_MB", "1")
+    ref, qb, qo = workloads.c2_reads_packed(23, seed=21)
+    rb, ro = packing.pack([ref])
+    ridx = np.zeros(23, np.int32)
+    got = emu_aligner.align_packed(rb, ro, ridx, qb, qo, 10, 3, 1, 0)
+    exp = oracle_port.align_batch(0, rb, ro, ridx, qb, qo, 10, 3, 1)
+    assert (got[3] == exp[3]).all() and (got[4] == exp[4]).all()
+    assert (got[0] == exp[0]).all() and (got[1] == exp[1]).all()      # incl. zero tails: oracle buffers start zeroed
+
+
 def test_emu_plan_interface_and_stats(emu_aligner, oracle_port):
     from gotoh_b200 import packing, workloads
     ref, qb, qo = workloads.c2_reads_packed(10, seed=3)
