@@ -185,6 +185,7 @@ struct gotoh_b200_plan {
     int64_t n_pairs = 0;
     int gip = 0, gep = 0, term = 1, matrix = 0;
     int ncls = 1;
+    int has_dollar = 0;
     int smin_m1 = 0;
     std::vector<Chunk> chunks;
     int n_launches = 0;
@@ -267,18 +268,21 @@ int host_threads(int64_t bytes) {
 }
 
 template <class V, int K, bool MULTI>
-int launch_forward_k(const gotoh_b200_plan* pl, const FwdParams& fp, int ntasks) {
+int launch_forward_k(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
     const Workspace* ws = pl->ws;
     const size_t per_warp = FwdSmem<V, K>::per_warp(pl->ncls);
-    const size_t smem = per_warp * FWD_WARPS;
-    if (smem > 200 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
+    // warps per CTA: 4 unless the query profile (1 KB per class per warp at K = 8) needs more room
+    int warps = FWD_WARPS;
+    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+    const size_t smem = per_warp * warps;
+    if (smem > 220 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
     CU(cudaFuncSetAttribute(k_forward<V, K, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid: enough CTAs to fill every SM, tasks are pulled from a counter
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));
-    int grid = std::min((ntasks + FWD_WARPS - 1) / FWD_WARPS, ws->sm_count * ctas_per_sm);
-    if (MULTI) grid = std::min<long long>(grid, (long long)ws->d_bnd.cap / (2 * pl->bnd_stride * FWD_WARPS));
+    int grid = std::min((ntasks + warps - 1) / warps, ws->sm_count * ctas_per_sm);
+    if (MULTI) grid = std::min<long long>(grid, (long long)ws->d_bnd.cap / (2 * pl->bnd_stride * warps));
     grid = std::max(grid, 1);
-    GOTOH_LAUNCH((k_forward<V, K, MULTI>), dim3(grid), dim3(FWD_WARPS * 32), smem, ws->stream, fp);
+    GOTOH_LAUNCH((k_forward<V, K, MULTI>), dim3(grid), dim3(warps * 32), smem, ws->stream, fp);
     CU(cudaGetLastError());
     return GOTOH_B200_OK;
 }
@@ -345,6 +349,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     uint8_t* h_ref_raw = ws->h_ref_raw.p;
     memset(h_ref_raw, 0, ref_total);
     bool ref_present[128] = {false}, qry_present[128] = {false};
+    bool any_dollar3 = false;
     for (size_t u = 0; u < nu; ++u) {
         const uint8_t* s = ref_bytes + ref_lo[u];
         uint8_t* dst = h_ref_raw + ref_pos[u];
@@ -355,9 +360,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
             if (degap && c == '-') continue;                       // degap(): gotoh.cpp:529-543
             if (c < 1 || c > 126) return fail(GOTOH_B200_EDOMAIN, "reference %lld: byte 0x%02x outside 1..126", (long long)used_refs[u], c);
             dollars = (c == '$') ? dollars + 1 : 0;
-            if (dollars >= 3 && pl->matrix == GOTOH_B200_NT)
-                return fail(GOTOH_B200_EDOMAIN, "reference %lld contains \"$$$\": the stop-codon bonus rule "
-                            "(gotoh.cpp:324-344) is not implemented on the device yet", (long long)used_refs[u]);
+            if (dollars >= 3) any_dollar3 = true;                  // stop-codon bonus rule applies (gotoh.cpp:324-344)
             ref_present[c] = true;
             dst[m++] = c;
         }
@@ -441,22 +444,51 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     });
 
     // ---- classes of reference bytes, compact table, score range ----------------------------
-    int cls_of[128];
-    std::vector<int> rep(1, 0);
-    for (int c = 0; c < 128; ++c) { cls_of[c] = 0; if (ref_present[c]) { cls_of[c] = (int)rep.size(); rep.push_back(c); } }
+    // A class is a distinct reference byte - or, in references that contain "$$$", a distinct
+    // (byte, rmask) where rmask says which of the three stop-codon bonus rules (gotoh.cpp:324-344)
+    // can fire in that row: bit0 a[i-3..i-1], bit1 a[i-2..i], bit2 a[i-1..i+1] == "$$$" (i >= 3).
+    // The +6 bonuses then live in the query profile and the kernel needs no extra work per cell.
+    uint8_t* h_ref_cls = ws->h_ref_cls.p;
+    memset(h_ref_cls, 0, ref_total);
+    int cls_of[128][8];
+    memset(cls_of, 0, sizeof(cls_of));
+    std::vector<int> rep(1, 0), rep_mask(1, 0);
+    for (size_t u = 0; u < nu; ++u) {
+        const uint8_t* a = h_ref_raw + ref_pos[u];
+        const int M = ref_len[u];
+        for (int i = 1; i <= M; ++i) {
+            int rm = 0;
+            if (any_dollar3 && i >= 3) {
+                auto dol = [&](int p0) { return p0 >= 0 && p0 + 2 < M && a[p0] == '$' && a[p0 + 1] == '$' && a[p0 + 2] == '$'; };
+                rm = (dol(i - 3) ? 1 : 0) | (dol(i - 2) ? 2 : 0) | (dol(i - 1) ? 4 : 0);
+            }
+            const int c = a[i - 1];
+            if (!cls_of[c][rm]) {
+                if (rep.size() >= 250) return fail(GOTOH_B200_ERANGE, "more than 249 reference byte classes");
+                cls_of[c][rm] = (int)rep.size(); rep.push_back(c); rep_mask.push_back(rm);
+            }
+            h_ref_cls[ref_pos[u] + i - 1] = (uint8_t)cls_of[c][rm];
+        }
+    }
     pl->ncls = (int)rep.size();
-    CU(ws->h_table4.ensure((size_t)pl->ncls * 128));
-    int32_t* h_table4 = ws->h_table4.p;
-    memset(h_table4, 0, (size_t)pl->ncls * 128 * sizeof(int32_t));
+    pl->has_dollar = any_dollar3 ? 1 : 0;
+    CU(ws->h_table4.ensure((size_t)pl->ncls * 136));
+    int32_t* h_table4 = ws->h_table4.p;           // [ncls][128] scores, then [ncls][8] bonuses
+    memset(h_table4, 0, (size_t)pl->ncls * 136 * sizeof(int32_t));
     int minT = 0, maxT = 0;
-    for (int c = 1; c < pl->ncls; ++c)
+    for (int c = 1; c < pl->ncls; ++c) {
         for (int b = 1; b < 127; ++b) {
             const int t = tab.v[rep[c]][b];
             h_table4[(size_t)c * 128 + b] = 4 * (t + 2 * pl->gep);
             if (qry_present[b]) { minT = std::min(minT, t); maxT = std::max(maxT, t); }
         }
-    uint8_t* h_ref_cls = ws->h_ref_cls.p;
-    for (size_t x = 0; x < ref_total; ++x) h_ref_cls[x] = (uint8_t)cls_of[h_ref_raw[x] & 127];
+        for (int cm = 0; cm < 8; ++cm) {
+            int bits = rep_mask[c] & cm, cnt = 0;
+            while (bits) { cnt += bits & 1; bits >>= 1; }
+            h_table4[(size_t)pl->ncls * 128 + (size_t)c * 8 + cm] = 4 * 6 * cnt;
+        }
+    }
+    if (any_dollar3) maxT += 18;                   // up to three +6 bonuses on one cell
 
     // ---- choose the path per pair, form warp tasks -------------------------------------------
     // Vec16 (two alignments per warp) needs: single strip (N <= 32*Kmax), same reference for both
@@ -568,7 +600,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     CU(ws->d_ref_raw.ensure(ref_total));
     CU(ws->d_ref_cls.ensure(ref_total));
     CU(ws->d_qry.ensure((size_t)qtotal + 64));
-    CU(ws->d_table4.ensure((size_t)pl->ncls * 128));
+    CU(ws->d_table4.ensure((size_t)pl->ncls * 136));
     CU(ws->d_pairs.ensure((size_t)n));
     CU(ws->d_tasks.ensure(n_tasks));
     CU(ws->d_score.ensure((size_t)n)); CU(ws->d_end_i.ensure((size_t)n)); CU(ws->d_end_j.ensure((size_t)n));
@@ -645,7 +677,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     CU(h2d(ws->d_ref_raw.p, h_ref_raw, ref_total));
     CU(h2d(ws->d_ref_cls.p, h_ref_cls, ref_total));
     CU(h2d(ws->d_qry.p, h_qry, (size_t)qtotal + 64));
-    CU(h2d(ws->d_table4.p, h_table4, (size_t)pl->ncls * 128 * sizeof(int32_t)));
+    CU(h2d(ws->d_table4.p, h_table4, (size_t)pl->ncls * 136 * sizeof(int32_t)));
     CU(h2d(ws->d_pairs.p, pairs, (size_t)n * sizeof(PairInfo)));
     CU(h2d(ws->d_tasks.p, tasks, n_tasks * sizeof(Task)));
     return GOTOH_B200_OK;
@@ -670,6 +702,8 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
             fp.task_first = L.task_first; fp.task_count = L.task_count;
             fp.ref_cls = ws->d_ref_cls.p; fp.qry = ws->d_qry.p; fp.table4 = ws->d_table4.p;
             fp.ncls = pl->ncls; fp.gip = pl->gip; fp.gep = pl->gep;
+            fp.has_dollar = pl->has_dollar;
+            fp.bonus4 = ws->d_table4.p + (size_t)pl->ncls * 128;
             fp.rebase_mask = L.rebase_mask; fp.smin_m1 = pl->smin_m1;
             fp.four = 4u;
             fp.dir = ws->d_dir.p;

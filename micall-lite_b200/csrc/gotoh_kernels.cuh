@@ -73,6 +73,8 @@ struct FwdParams {
     const uint8_t* ref_cls;     // class index per reference position (0 = padding class)
     const uint8_t* qry;
     const int32_t* table4;      // [ncls][128] : 4*(T[rep(c)][b] + 2*gep), row 0 unused
+    const int32_t* bonus4;      // [ncls][8] : 4*6*popcount(rmask(c) & cmask) stop-codon bonuses (gotoh.cpp:324-344)
+    int32_t has_dollar;         // some reference contains "$$$"
     int32_t ncls;               // number of classes incl. the padding class 0
     int32_t gip, gep;
     int32_t rebase_mask;        // Vec16: R-1 (R power of two); Vec32: unused
@@ -155,6 +157,17 @@ __device__ __forceinline__ DirAddr dir_addr(const PairInfo& p, int i, int j) {
 // ------------------------------------------------------------------------------------
 // K1/K2/K3  forward DP
 // ------------------------------------------------------------------------------------
+// Which of the three stop-codon windows around column j (1-based) of query b[0..N) hold TAG/TAA/TGA.
+__device__ __forceinline__ bool is_stop3(const uint8_t* b, int N, int p0) {
+    if (p0 < 0 || p0 + 2 > N - 1) return false;   // reads past the end hit the terminator in the reference
+    const uint8_t x = b[p0], y = b[p0 + 1], z = b[p0 + 2];
+    return x == 'T' && ((y == 'A' && (z == 'G' || z == 'A')) || (y == 'G' && z == 'A'));
+}
+__device__ __forceinline__ int stop_mask(const uint8_t* b, int N, int j) {
+    if (j < 3 || j > N) return 0;
+    return (is_stop3(b, N, j - 3) ? 1 : 0) | (is_stop3(b, N, j - 2) ? 2 : 0) | (is_stop3(b, N, j - 1) ? 4 : 0);
+}
+
 template <class V, int K>
 struct FwdSmem {
     enum { K4 = (K + 3) / 4 };
@@ -178,7 +191,8 @@ struct Wave {
     int2* ring;
     const int2* bnd_in;
     int2* bnd_out;
-    T c_up, c_sl0, c_q0, c_g4;
+    T c_up, c_sl0, c_q0, c_g4, c_g4_lane0;
+    unsigned keep, inj_s, inj_q;   // lane-0 injection of column 0
     T Uq[K];
 
     // ---- lane state ------------------------------------------------------------------------
@@ -202,7 +216,7 @@ struct Wave {
             P[k] = V::pack(ja * g4 + 1, jb * g4 + 1);
         }
         Sd_in = V::pack(min(j0, Na) * g4, min(j0, Nb) * g4);   // S^(0, j0)
-        diag0 = V::both(0);                                     // 4*(i-1)*g at i = 1
+        diag0 = V::both(0);                                     // 4*(i-1)*g at i = 1 (stays 0 outside lane 0)
         // seed below any reachable score, expressed in the row-0 frame of column N
         best = V::pack(4 * smin_m1 + Na * g4, 4 * smin_m1 + Nb * g4);
         best_i_a = best_i_b = 0;
@@ -235,8 +249,13 @@ struct Wave {
                 const int2 b = ring[(((t - 1) >> 5) & 1) * 32 + ((t - 1) & 31)];
                 Sl = (T)b.x; Ql = (T)b.y;
             }
-        } else if (lane == 0) {
-            Sl = c_sl0; Ql = c_q0; sdiag = diag0;           // column 0 (gotoh.cpp:290-293)
+        } else {
+            // column 0 (gotoh.cpp:290-293) is injected into lane 0.  Written as x*keep + inj (keep = 0 for
+            // lane 0, 1 elsewhere; inj = 0 outside lane 0) so that it issues as IMAD on the FMA pipe
+            // instead of three selects on the saturated ALU pipe.
+            Sl = (T)(V::raw(Sl) * keep + inj_s);
+            Ql = (T)(V::raw(Ql) * keep + inj_q);
+            sdiag = (T)(V::raw(sdiag) * keep + V::raw(diag0));
         }
 
         // ---- int16 range control: rebase every R rows (Vec16 only) --------------------------
@@ -246,7 +265,7 @@ struct Wave {
 #pragma unroll
                 for (int k = 0; k < K; ++k) { S[k] = V::add(S[k], d); P[k] = V::add(P[k], d); }
                 sdiag = V::add(sdiag, d);
-                diag0 = V::add(diag0, d);
+                if (lane == 0) diag0 = V::add(diag0, d);
                 best = V::add(best, d);
             }
         }
@@ -279,7 +298,7 @@ struct Wave {
         }
         sendS = S[K - 1];
         sendQ = q;
-        if (!MULTI || strip == 0) diag0 = V::add(diag0, c_g4);
+        if (!MULTI || strip == 0) diag0 = V::add(diag0, c_g4_lane0);
 
         // ---- directions: 2K bits per alignment per lane-step -------------------------------------
         const unsigned dstep = accC - accS;
@@ -362,6 +381,10 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
     w.c_sl0 = V::both(u4);             // column 0 seen by the Q recurrence: s~ = u   (gotoh.cpp:291)
     w.c_q0 = V::both(2 * u4 + 2);      //                                     q~ = 2u  (gotoh.cpp:293)
     w.c_g4 = V::both(w.g4);
+    w.c_g4_lane0 = lane == 0 ? w.c_g4 : V::both(0);
+    w.keep = (p.four >> 2) - (lane == 0 ? 1u : 0u);   // 0 for lane 0, 1 elsewhere; opaque so x*keep stays an IMAD
+    w.inj_s = lane == 0 ? V::raw(w.c_sl0) : 0u;
+    w.inj_q = lane == 0 ? V::raw(w.c_q0) : 0u;
 
     for (;;) {
         // ---- dynamic task fetch (one atomic per warp) ---------------------------------------
@@ -379,7 +402,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
         const int nblk = pa.nblk;
         const uint8_t* qa = p.qry + pa.qry_pos;
         const uint8_t* qb = p.qry + pb.qry_pos;
-        int2* bnd0 = MULTI ? p.bnd + ((int64_t)(blockIdx.x * FWD_WARPS + warp) * 2) * p.bnd_stride : nullptr;
+        int2* bnd0 = MULTI ? p.bnd + ((int64_t)(blockIdx.x * (blockDim.x >> 5) + warp) * 2) * p.bnd_stride : nullptr;
         w.M = M; w.Na = Na; w.Nb = Nb;
         w.cls = p.ref_cls + pa.ref_pos;
         w.lr_best_a = w.lr_best_b = -2147483647;
@@ -402,18 +425,35 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
                 const bool real_a = (j0 + k) < Na, real_b = (j0 + k) < Nb;
                 w.Uq[k] = V::pack(real_a ? u4 + 2 : 3, real_b ? u4 + 2 : 3);
             }
+            // stop-codon masks of this lane's columns (only when some reference holds "$$$"):
+            // bit0 b[j-3..j-1], bit1 b[j-2..j], bit2 b[j-1..j+1] in {TAG,TAA,TGA}, j >= 3 (gotoh.cpp:324-344)
+            int cm_a[K], cm_b[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { cm_a[k] = 0; cm_b[k] = 0; }
+            if (p.has_dollar) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    cm_a[k] = stop_mask(qa, Na, j0 + k + 1);
+                    if (NP == 2) cm_b[k] = stop_mask(qb, Nb, j0 + k + 1);
+                }
+            }
             for (int c = 0; c < p.ncls; ++c) {
                 const int32_t* trow = p.table4 + c * 128;
+                const int32_t* brow = p.bonus4 + c * 8;
 #pragma unroll
                 for (int kq = 0; kq < K4; ++kq) {
                     unsigned e[4];
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const int ja = j0 + kq * 4 + kk;
+                        const int k = kq * 4 + kk;
+                        const int ja = j0 + k;
                         // padding columns (beyond N) use E = 4u so that they clone column N
-                        const int ea = (ja < Na) ? trow[qa[ja]] : u4;
-                        const int eb = (NP == 2) ? ((ja < Nb) ? trow[qb[ja]] : u4) : 0;
-                        e[kk] = V::raw(V::pack(ea, eb));
+                        int ea = u4, eb = u4;
+                        if (k < K) {
+                            if (ja < Na) ea = trow[qa[ja]] + (p.has_dollar ? brow[cm_a[k]] : 0);
+                            if (NP == 2 && ja < Nb) eb = trow[qb[ja]] + (p.has_dollar ? brow[cm_b[k]] : 0);
+                        }
+                        e[kk] = V::raw(V::pack(ea, NP == 2 ? eb : 0));
                     }
                     prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
                 }

@@ -49,7 +49,7 @@ def matches(case, got):
     return sha(oa) == case["sha_a"] and sha(ob) == case["sha_b"]
 
 
-def run_cases(aligner, cases, max_cells=None, skip_dollar=True):
+def run_cases(aligner, cases, max_cells=None, skip_dollar=False):
     """Align golden cases through an Aligner, batched per parameter set.  Returns mismatching cases."""
     groups = {}
     for c in cases:

@@ -52,6 +52,41 @@ def test_emu_chunked_arena_and_mixed_batch(emu_aligner, oracle_port, monkeypatch
         assert got[k] == oracle_port.align_it(refs[ridx[k]], queries[k], 10, 3, 1), k
 
 
+def test_emu_stop_codon_bonus_rule(emu_aligner, oracle_port, forced_path):
+    """SURVEY 8f next #4: the "$$$" stop-codon bonus (gotoh.cpp:324-344) lives in the query profile."""
+    rng = random.Random(31)
+    refs, qs = [], []
+    for _ in range(300):
+        a = "".join(rng.choice("ACGT") for _ in range(rng.randint(3, 60)))
+        for _ in range(rng.randint(1, 3)):
+            p = rng.randrange(len(a) + 1)
+            a = a[:p] + rng.choice(["$$$", "$$$$", "$$", "$$$$$$"]) + a[p:]
+        b = a.replace("$$$", rng.choice(["TAG", "TAA", "TGA", "TGG"]))
+        b = list(b.replace("$", rng.choice("ACGT")))
+        for _ in range(rng.randint(0, 3)):
+            b[rng.randrange(len(b))] = rng.choice("ACGTTAG")
+        refs.append(a)
+        qs.append("".join(b))
+    for gip, gep, term in [(10, 3, 1), (0, 0, 0), (5, 1, 0)]:
+        got = emu_aligner.align_batch(refs, qs, gip, gep, term, 0)
+        for k in range(len(refs)):
+            assert got[k] == oracle_port.align_it(refs[k], qs[k], gip, gep, term), (refs[k], qs[k], gip, gep, term)
+    # the rule sits in align() itself, so it also fires under the amino-acid tables
+    assert emu_aligner.align_it_aa("KF$$$R", "KFTAGR", 40, 10, 1) == oracle_port.align_it_aa("KF$$$R", "KFTAGR", 40, 10, 1)
+
+
+def test_emu_many_reference_byte_classes(emu_aligner, oracle_port):
+    """A reference using ~120 distinct bytes needs a 120-class query profile: the launcher drops to
+    fewer warps per CTA instead of failing."""
+    rng = random.Random(8)
+    alpha = [chr(c) for c in range(1, 127) if chr(c) not in " \t\n\r$"]
+    ref = "".join(alpha) + "".join(rng.choice(alpha) for _ in range(100))
+    qs = ["".join(rng.choice(alpha) for _ in range(rng.randint(5, 90))) for _ in range(12)]
+    got = emu_aligner.align_batch(ref, qs, 10, 3, 1, 0)
+    for q, g in zip(qs, got):
+        assert g == oracle_port.align_it(ref, q, 10, 3, 1)
+
+
 def test_emu_slab_pipeline_many_slabs(emu_aligner, oracle_port, monkeypatch):
     """The one-shot call cuts the batch into slabs that ping-pong between two workspaces; force
     one slab per handful of pairs and check order, contents and the zeroed stride tails."""

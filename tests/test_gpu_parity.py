@@ -133,6 +133,31 @@ def test_gpu_paths_agree_and_order_invariance_at_scale(gpu_aligner, monkeypatch)
         assert not ((ar == 45) & (aq == 45)).any()
 
 
+def test_gpu_stop_codon_bonus_and_many_classes(gpu_aligner, oracle_port, forced_path):
+    rng = random.Random(32)
+    refs, qs = [], []
+    for _ in range(2000):
+        a = "".join(rng.choice("ACGT") for _ in range(rng.randint(3, 200)))
+        for _ in range(rng.randint(1, 3)):
+            p = rng.randrange(len(a) + 1)
+            a = a[:p] + rng.choice(["$$$", "$$$$", "$$", "$$$$$$"]) + a[p:]
+        b = list(a.replace("$$$", rng.choice(["TAG", "TAA", "TGA", "TGG"])).replace("$", "A"))
+        for _ in range(rng.randint(0, 3)):
+            b[rng.randrange(len(b))] = rng.choice("ACGTTAG")
+        refs.append(a)
+        qs.append("".join(b))
+    from gotoh_b200 import packing
+    rb, ro = packing.pack(refs)
+    qb, qo = packing.pack(qs)
+    _check_packed(gpu_aligner, oracle_port, 0, rb, ro, None, qb, qo, 10, 3, 1)
+    alpha = [chr(c) for c in range(1, 127) if chr(c) not in " \t\n\r$"]
+    ref = "".join(alpha) + "".join(rng.choice(alpha) for _ in range(300))
+    qs = ["".join(rng.choice(alpha) for _ in range(rng.randint(5, 400))) for _ in range(200)]
+    got = gpu_aligner.align_batch(ref, qs, 10, 3, 1, 0)
+    for q, g in zip(qs, got):
+        assert g == oracle_port.align_it(ref, q, 10, 3, 1)
+
+
 def test_gpu_chunked_arena(gpu_aligner, oracle_port, monkeypatch):
     from gotoh_b200 import packing, workloads
     monkeypatch.setenv("GOTOH_B200_ARENA_MB", "8")
