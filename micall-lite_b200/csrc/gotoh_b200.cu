@@ -278,11 +278,25 @@ int launch_forward_k(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
     if (smem > 220 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
     CU(cudaFuncSetAttribute(k_forward<V, K, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid: enough CTAs to fill every SM, tasks are pulled from a counter
-    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1)));
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(GOTOH_MIN_CTAS, (200 * 1024) / std::max<size_t>(smem, 1)));
     int grid = std::min((ntasks + warps - 1) / warps, ws->sm_count * ctas_per_sm);
     if (MULTI) grid = std::min<long long>(grid, (long long)ws->d_bnd.cap / (2 * pl->bnd_stride * warps));
     grid = std::max(grid, 1);
     GOTOH_LAUNCH((k_forward<V, K, MULTI>), dim3(grid), dim3(warps * 32), smem, ws->stream, fp);
+    CU(cudaGetLastError());
+    return GOTOH_B200_OK;
+}
+
+int launch_forward_cta(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
+    const Workspace* ws = pl->ws;
+    const size_t per_warp = (size_t)pl->ncls * 2 * 32 * 16 + 256 * sizeof(int2);    // K = 8 profile + boundary ring
+    const size_t smem = per_warp * FWD_WARPS;
+    if (smem > 200 * 1024) return -1;       // caller falls back to the warp-serial multi-strip kernel
+    CU(cudaFuncSetAttribute(k_forward_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(GOTOH_MIN_CTAS, (200 * 1024) / smem));
+    int grid = std::max(1, std::min(ntasks, ws->sm_count * ctas_per_sm));
+    grid = (int)std::min<long long>(grid, std::max<long long>(1, (long long)ws->d_bnd.cap / (2 * pl->bnd_stride)));
+    GOTOH_LAUNCH((k_forward_cta<8>), dim3(grid), dim3(FWD_WARPS * 32), smem, ws->stream, fp);
     CU(cudaGetLastError());
     return GOTOH_B200_OK;
 }
@@ -617,7 +631,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     if (any_multi) {
         // multi-strip boundary columns: two int2 columns of maxM+2 rows per resident warp
         pl->bnd_stride = ((int64_t)maxM + 2 + 15) & ~15LL;
-        const int64_t slots = (int64_t)ws->sm_count * 4 * FWD_WARPS;
+        const int64_t slots = (int64_t)ws->sm_count * GOTOH_MIN_CTAS * FWD_WARPS;
         CU(ws->d_bnd.ensure((size_t)(slots * 2 * pl->bnd_stride)));
     }
     int64_t budget = pl->arena_budget_bytes;
@@ -711,9 +725,19 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
             fp.score = ws->d_score.p; fp.end_i = ws->d_end_i.p; fp.end_j = ws->d_end_j.p;
             fp.work_counter = ws->d_counter.p + launch_no++;
             // multi-strip tasks only exist with K = 8 (pick_K), and only on the int32 path
-            const int rc = L.x2 ? launch_forward<Vec16, false>(pl, fp, L.K, L.task_count)
-                         : (L.multi_strip ? launch_forward_k<Vec32, 8, true>(pl, fp, L.task_count)
-                                          : launch_forward<Vec32, false>(pl, fp, L.K, L.task_count));
+            int rc;
+            if (L.x2) rc = launch_forward<Vec16, false>(pl, fp, L.K, L.task_count);
+            else if (!L.multi_strip) rc = launch_forward<Vec32, false>(pl, fp, L.K, L.task_count);
+            else {
+                // K2: with fewer long pairs than resident warps a CTA per pair (4 warps pipelined over
+                // adjacent strips) keeps the SMs full; with plenty of pairs one warp per pair has no
+                // synchronisation at all.  GOTOH_B200_LONG=cta|warp pins the choice (tests).
+                const char* pin = getenv("GOTOH_B200_LONG");
+                bool cta = L.task_count < ws->sm_count * GOTOH_MIN_CTAS * FWD_WARPS;
+                if (pin) cta = (pin[0] == 'c');
+                rc = cta ? launch_forward_cta(pl, fp, L.task_count) : -1;
+                if (rc == -1) rc = launch_forward_k<Vec32, 8, true>(pl, fp, L.task_count);
+            }
             if (rc) return rc;
         }
         if (timed && forward_ms) CU(cudaEventRecord(ws->ev[3], ws->stream));

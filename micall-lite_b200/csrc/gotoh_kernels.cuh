@@ -41,6 +41,9 @@ namespace gotoh {
 
 enum { DIR_DIAG = 0, DIR_UP = 1, DIR_LEFT = 2 };
 enum { FWD_WARPS = 4 };          // warps per CTA in k_forward
+#ifndef GOTOH_MIN_CTAS
+#define GOTOH_MIN_CTAS 4         // resident CTAs per SM the forward kernel is compiled for (register cap 65536/(128*N))
+#endif
 enum { REF_PAD = 64 };           // class bytes of padding on both sides of every reference
 enum { PAD_CLASS = 0 };
 
@@ -177,10 +180,22 @@ struct FwdSmem {
 
 // State of one warp sweeping one strip (32*K query columns) down the reference.
 // Every member is a register after inlining; all indexing is static.
-template <class V, int K, bool MULTI>
+__device__ __forceinline__ void gotoh_pause() {
+#ifdef GOTOH_SIMT_EMU
+    simt::yield();
+#else
+    __nanosleep(40);
+#endif
+}
+
+// MODE 0: the query fits one strip.  MODE 1: one warp walks the strips one after another, boundary
+// columns through global memory.  MODE 2 (K2, long pairs): the 4 warps of a CTA work on adjacent strips
+// of ONE pair at the same time, each ~64 rows behind its left neighbour - an anti-diagonal wavefront
+// across the CTA - handing boundary columns over through shared-memory rings.
+template <class V, int K, int MODE>
 struct Wave {
     typedef typename V::T T;
-    enum { K4 = (K + 3) / 4, STEPS = V::STEPS, NP = V::NPAIR };
+    enum { K4 = (K + 3) / 4, STEPS = V::STEPS, NP = V::NPAIR, MULTI = (MODE != 0), CTA = (MODE == 2), XR = 256 };
 
     // ---- per-task / per-strip constants --------------------------------------------------
     int lane, M, Na, Nb, j0, strip, gep, g4, rebase_mask, smin_m1;
@@ -191,6 +206,19 @@ struct Wave {
     int2* ring;
     const int2* bnd_in;
     int2* bnd_out;
+    // MODE 2: rings of XR rows in shared memory + published/consumed row sequence numbers
+    const int2* xin;
+    int2* xout;
+    volatile long long* pub_in;    // producer of my left boundary: rows published
+    volatile long long* cons_in;   //   ... and where I tell it how far I have consumed
+    volatile long long* pub_out;   // my own ring
+    volatile long long* cons_out;
+    long long seq_in, seq_out;     // round * M of the producer's / my current strip
+    // The hand-over from the LAST warp of a round to warp 0 of the next round cannot be a ring: warp 0
+    // only starts its next strip after finishing the current one, a whole column later.  That link is a
+    // full-length column in global memory (pub only, no back-pressure: warp 0 is always ahead of it).
+    int2* col;
+    bool in_col, out_col;
     T c_up, c_sl0, c_q0, c_g4, c_g4_lane0;
     unsigned keep, inj_s, inj_q;   // lane-0 injection of column 0
     T Uq[K];
@@ -235,7 +263,14 @@ struct Wave {
         T Sl = __shfl_up_sync(0xffffffffu, sendS, 1);
         T Ql = __shfl_up_sync(0xffffffffu, sendQ, 1);
         T sdiag = Sd_in;
-        if (MULTI && strip > 0) {
+        if (CTA && strip > 0) {
+            // lane 0 is at row t; the producer warp published it (block() waited for that)
+            if (lane == 0) {
+                const long long raw = in_col ? *reinterpret_cast<const volatile long long*>(&col[min(t, M)])
+                                             : *reinterpret_cast<const volatile long long*>(&xin[t & (XR - 1)]);
+                Sl = (T)(int)(raw & 0xffffffffLL); Ql = (T)(int)(raw >> 32);
+            }
+        } else if (MULTI && strip > 0) {
             // boundary column written by the previous strip; staged 32 rows at a time
             if (((t - 1) & 31) == 0) {
                 __syncwarp();
@@ -253,9 +288,13 @@ struct Wave {
             // column 0 (gotoh.cpp:290-293) is injected into lane 0.  Written as x*keep + inj (keep = 0 for
             // lane 0, 1 elsewhere; inj = 0 outside lane 0) so that it issues as IMAD on the FMA pipe
             // instead of three selects on the saturated ALU pipe.
+#ifdef GOTOH_LANE0_SEL
+            if (lane == 0) { Sl = c_sl0; Ql = c_q0; sdiag = diag0; }
+#else
             Sl = (T)(V::raw(Sl) * keep + inj_s);
             Ql = (T)(V::raw(Ql) * keep + inj_q);
             sdiag = (T)(V::raw(sdiag) * keep + V::raw(diag0));
+#endif
         }
 
         // ---- int16 range control: rebase every R rows (Vec16 only) --------------------------
@@ -326,8 +365,14 @@ struct Wave {
             }
         }
         // ---- boundary column for the next strip --------------------------------------------------
-        if (MULTI && !last_strip && lane == 31 && i >= 1 && i <= M)
-            bnd_out[i] = make_int2((int)V::raw(S[K - 1]), (int)V::raw(q));
+        if (MULTI && !last_strip && lane == 31 && i >= 1 && i <= M) {
+            if (CTA) {
+                const long long v = (long long)(((unsigned long long)V::raw(q) << 32) | V::raw(S[K - 1]));
+                if (out_col) *reinterpret_cast<volatile long long*>(&col[i]) = v;
+                else *reinterpret_cast<volatile long long*>(&xout[i & (XR - 1)]) = v;
+            }
+            else bnd_out[i] = make_int2((int)V::raw(S[K - 1]), (int)V::raw(q));
+        }
 
         if (SLOW) {
             // row 0: re-initialise the lane just before its first real row
@@ -351,16 +396,45 @@ struct Wave {
 
     template <bool SLOW>
     __device__ __forceinline__ void block(const int tb, uint4* dst) {
+        const int t0 = tb * STEPS + 1, hi = t0 + STEPS - 1;
+        if (CTA) {
+            if (strip > 0 && ((t0 - 1) & 31) == 0) {
+                // lane 0 consumes rows t0 .. t0+31 during the next 32 steps: wait until they are published,
+                // and tell the producer that everything before t0 has been consumed
+                if (lane == 0) {
+                    const long long need = seq_in + min(t0 + 31, M);
+                    while (*pub_in < need) gotoh_pause();
+                    *cons_in = seq_in + (t0 - 1);
+                }
+                __syncwarp();
+            }
+            if (!last_strip && !out_col && hi - 31 >= 1) {
+                // lane 31 writes rows up to hi-31 in this block; their ring slots held rows XR earlier
+                // (or the previous round's strip, which must be consumed completely)
+                if (lane == 31) {
+                    const long long must = seq_out + max(0, min(hi - 31, M) - XR);
+                    while (*cons_out < must) gotoh_pause();
+                }
+                __syncwarp();
+            }
+        }
 #pragma unroll
         for (int s = 0; s < STEPS; ++s) step<SLOW>(tb * STEPS + s + 1, s);
         *dst = dwords;   // one coalesced 512-byte store per warp per STEPS lane-steps
+        if (CTA && !last_strip) {
+            __syncwarp();
+            if (lane == 31) {
+                __threadfence_block();
+                *pub_out = seq_out + min(max(hi - 31, 0), M);
+            }
+        }
     }
 };
 
 template <class V, int K, bool MULTI>
-__global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
+__global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(const FwdParams p) {
     typedef typename V::T T;
-    typedef Wave<V, K, MULTI> W;
+    typedef Wave<V, K, MULTI ? 1 : 0> W;
     enum { K4 = W::K4, STEPS = V::STEPS, NP = V::NPAIR };
     GOTOH_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -514,6 +588,158 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) k_forward(const FwdParams p) {
                     if (lr_best_b > best_b) { p.score[task.pair_b] = lr_best_b; p.end_i[task.pair_b] = M; p.end_j[task.pair_b] = lr_j_b; }
                     else { p.score[task.pair_b] = best_b; p.end_i[task.pair_b] = bi_b; p.end_j[task.pair_b] = Nb; }
                 }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K2  long pairs: one CTA per pair, anti-diagonal wavefront across its 4 warps (int32 cells)
+// ------------------------------------------------------------------------------------
+// Warp w takes strips w, w+4, w+8, ... of 256 query columns.  Strip s+1 can start as soon as strip s
+// has published its first 32 boundary rows, so the four warps run ~64 rows apart; boundary columns
+// never touch global memory.  Same cell code, same direction layout, same epilogue as k_forward.
+template <int K>
+__global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_cta(const FwdParams p) {
+    typedef Vec32 V;
+    typedef Wave<V, K, 2> W;
+    enum { K4 = W::K4, STEPS = V::STEPS, XR = W::XR };
+    GOTOH_DYN_SMEM(smem_raw);
+    __shared__ long long sh_pub[FWD_WARPS], sh_cons[FWD_WARPS];
+    __shared__ int sh_task;
+    __shared__ int sh_lr_best[FWD_WARPS], sh_lr_j[FWD_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t prof_bytes = (size_t)p.ncls * K4 * 32 * 16;
+    unsigned char* my_smem = smem_raw + (size_t)warp * (prof_bytes + XR * sizeof(int2));
+    uint4* prof = reinterpret_cast<uint4*>(my_smem);
+
+    W w;
+    w.lane = lane;
+    w.gep = p.gep;
+    w.g4 = 4 * p.gep;
+    w.rebase_mask = p.rebase_mask;
+    w.smin_m1 = p.smin_m1;
+    w.four = p.four;
+    w.prof_lane = prof + lane;
+    w.ring = nullptr;
+    w.bnd_in = nullptr;
+    w.bnd_out = nullptr;
+    const int u4 = -4 * p.gip;
+    w.c_up = V::both(u4 + 1);
+    w.c_sl0 = V::both(u4);
+    w.c_q0 = V::both(2 * u4 + 2);
+    w.c_g4 = V::both(w.g4);
+    w.c_g4_lane0 = lane == 0 ? w.c_g4 : V::both(0);
+    w.keep = (p.four >> 2) - (lane == 0 ? 1u : 0u);
+    w.inj_s = lane == 0 ? V::raw(w.c_sl0) : 0u;
+    w.inj_q = lane == 0 ? V::raw(w.c_q0) : 0u;
+    const int pw = (warp + FWD_WARPS - 1) % FWD_WARPS;      // the warp that produces my left boundary
+    w.xout = reinterpret_cast<int2*>(my_smem + prof_bytes);
+    w.xin = reinterpret_cast<const int2*>(smem_raw + (size_t)pw * (prof_bytes + XR * sizeof(int2)) + prof_bytes);
+    w.pub_out = &sh_pub[warp];
+    w.cons_out = &sh_cons[warp];
+    w.pub_in = &sh_pub[pw];
+    w.cons_in = &sh_cons[pw];
+    w.col = p.bnd + (int64_t)blockIdx.x * 2 * p.bnd_stride;
+    w.in_col = (warp == 0);                      // strips 4r (r > 0) read the column written by strip 4r-1
+    w.out_col = (warp == FWD_WARPS - 1);         // strips 4r+3 write it
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh_task = (int)atomicAdd(p.work_counter, 1u);
+        if (threadIdx.x < FWD_WARPS) { sh_pub[threadIdx.x] = 0; sh_cons[threadIdx.x] = 0; }
+        __syncthreads();
+        const int tsk = sh_task;
+        if (tsk >= p.task_count) break;
+        const Task task = p.tasks[p.task_first + tsk];
+        const PairInfo pa = p.pairs[task.pair_a];
+        const int M = pa.M, Na = pa.N;
+        const int nstrips = (Na + 32 * K - 1) / (32 * K);
+        const int nblk = pa.nblk;
+        const uint8_t* qa = p.qry + pa.qry_pos;
+        w.M = M; w.Na = Na; w.Nb = Na;
+        w.cls = p.ref_cls + pa.ref_pos;
+        w.lr_best_a = w.lr_best_b = -2147483647;
+        w.lr_j_a = w.lr_j_b = 0;
+        w.best = V::both(0);
+        w.best_i_a = w.best_i_b = 0;
+
+        for (int strip = warp; strip < nstrips; strip += FWD_WARPS) {
+            const int j0 = (strip * 32 + lane) * K;
+            w.strip = strip;
+            w.j0 = j0;
+            w.last_strip = (strip == nstrips - 1);
+            w.seq_out = (long long)(strip / FWD_WARPS) * M;
+            w.seq_in = (long long)((strip - 1) / FWD_WARPS) * M;      // unused for strip 0
+
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K; ++k) w.Uq[k] = V::both((j0 + k) < Na ? u4 + 2 : 3);
+            int cm_a[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) cm_a[k] = p.has_dollar ? stop_mask(qa, Na, j0 + k + 1) : 0;
+            for (int c = 0; c < p.ncls; ++c) {
+                const int32_t* trow = p.table4 + c * 128;
+                const int32_t* brow = p.bonus4 + c * 8;
+#pragma unroll
+                for (int kq = 0; kq < K4; ++kq) {
+                    unsigned e[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int k = kq * 4 + kk;
+                        const int ja = j0 + k;
+                        int ea = u4;
+                        if (k < K && ja < Na) ea = trow[qa[ja]] + (p.has_dollar ? brow[cm_a[k]] : 0);
+                        e[kk] = (unsigned)ea;
+                    }
+                    prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
+                }
+            }
+            __syncwarp();
+
+            w.sendS = V::both(0);
+            w.sendQ = V::both(0);
+            w.dwords = make_uint4(0, 0, 0, 0);
+            w.row0_init();
+            w.next_cls = w.cls[-lane];
+
+            uint4* dst = p.dir + pa.dir_off + (int64_t)strip * nblk * 32 + lane;
+            for (int tb = 0; tb < nblk; ++tb, dst += 32) {
+                const int t0 = tb * STEPS + 1, hi = t0 + STEPS - 1;
+                const bool slow = (t0 <= 31) || (hi >= M);
+                if (slow) w.template block<true>(tb, dst);
+                else w.template block<false>(tb, dst);
+            }
+            // everything of the left boundary has been consumed
+            if (strip > 0 && lane == 0) *w.cons_in = w.seq_in + M;
+            __syncwarp();
+        }
+
+        // ---- epilogue: last row over all strips (every warp contributes), last column from the
+        //      warp that ran the last strip ------------------------------------------------------
+        int lr_best = w.lr_best_a, lr_j = w.lr_j_a;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int os = __shfl_xor_sync(0xffffffffu, lr_best, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, lr_j, off);
+            if (os > lr_best || (os == lr_best && oj > lr_j)) { lr_best = os; lr_j = oj; }
+        }
+        if (lane == 0) { sh_lr_best[warp] = lr_best; sh_lr_j[warp] = lr_j; }
+        __syncthreads();
+        const int last_warp = (nstrips - 1) % FWD_WARPS;
+        if (warp == last_warp) {
+            for (int x = 0; x < FWD_WARPS; ++x) {
+                const int os = sh_lr_best[x], oj = sh_lr_j[x];
+                if (os > lr_best || (os == lr_best && oj > lr_j)) { lr_best = os; lr_j = oj; }
+            }
+            const int i_fin = nblk * STEPS - lane;
+            const int la = (Na - 1) / K - (nstrips - 1) * 32;
+            int best_a = (V::lo(w.best) >> 2) - (i_fin + Na) * p.gep;
+            best_a = __shfl_sync(0xffffffffu, best_a, la);
+            const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a, la);
+            if (lane == 0) {
+                if (lr_best > best_a) { p.score[task.pair_a] = lr_best; p.end_i[task.pair_a] = M; p.end_j[task.pair_a] = lr_j; }
+                else { p.score[task.pair_a] = best_a; p.end_i[task.pair_a] = bi_a; p.end_j[task.pair_a] = Na; }
             }
         }
     }

@@ -184,6 +184,8 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 static inline void __threadfence() {}
+static inline void __threadfence_block() {}
+static inline void __nanosleep(unsigned) { simt::yield(); }
 
 // DPX (sm_90+/sm_100a: VIADDMNMX, VIMNMX3 and their .S16x2 forms)
 static inline int __viaddmax_s32(int a, int b, int c) { return max((int)((unsigned)a + (unsigned)b), c); }

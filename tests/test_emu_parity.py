@@ -87,6 +87,25 @@ def test_emu_many_reference_byte_classes(emu_aligner, oracle_port):
         assert g == oracle_port.align_it(ref, q, 10, 3, 1)
 
 
+@pytest.mark.parametrize("long_mode", ["cta", "warp"])
+def test_emu_long_pairs_cta_wavefront_and_warp_strips(emu_aligner, oracle_port, monkeypatch, long_mode):
+    """K2: queries wider than 256 columns.  'cta' = one CTA per pair, 4 warps pipelined over adjacent
+    strips (shared-memory rings + the cross-round column); 'warp' = one warp walks the strips."""
+    monkeypatch.setenv("GOTOH_B200_LONG", long_mode)
+    rng = random.Random(12)
+    refs, qs = [], []
+    for M, N in [(600, 1100), (520, 2100), (900, 257), (1500, 1300), (40, 3000), (700, 1025), (512, 1024), (300, 2600)]:
+        a = "".join(rng.choice("ACGT") for _ in range(M))
+        b = list((a * (N // M + 2))[:N])
+        for _ in range(N // 15):
+            b[rng.randrange(N)] = rng.choice("ACGTN")
+        refs.append(a)
+        qs.append("".join(b))
+    got = emu_aligner.align_batch(refs, qs, 15, 3, 1, 0)
+    for k in range(len(refs)):
+        assert got[k] == oracle_port.align_it(refs[k], qs[k], 15, 3, 1), (long_mode, len(refs[k]), len(qs[k]))
+
+
 def test_emu_slab_pipeline_many_slabs(emu_aligner, oracle_port, monkeypatch):
     """The one-shot call cuts the batch into slabs that ping-pong between two workspaces; force
     one slab per handful of pairs and check order, contents and the zeroed stride tails."""

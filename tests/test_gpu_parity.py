@@ -69,12 +69,28 @@ def test_gpu_c3_amino_vs_oracle(gpu_aligner, oracle_port, term, forced_path):
     _check_packed(gpu_aligner, oracle_port, 1, rb, ro, ridx, qb, qo, 40, 10, term)
 
 
-def test_gpu_c4_long_pairs_vs_oracle(gpu_aligner, oracle_port):
-    """C4 shape: ~9.6 kb x ~9.6 kb, 38 strips of 256 columns per pair, IUPAC codes in the refs."""
+@pytest.mark.parametrize("long_mode", ["cta", "warp"])
+def test_gpu_c4_long_pairs_vs_oracle(gpu_aligner, oracle_port, monkeypatch, long_mode):
+    """C4 shape: ~9.6 kb x ~9.6 kb, 38 strips of 256 columns per pair, IUPAC codes in the refs; both
+    long-pair kernels (CTA wavefront / warp-serial strips)."""
     from gotoh_b200 import packing, workloads
+    monkeypatch.setenv("GOTOH_B200_LONG", long_mode)
     refs, ridx, qb, qo = workloads.c4_pairs_packed(12, seed=44)
     rb, ro = packing.pack(refs)
     _check_packed(gpu_aligner, oracle_port, 0, rb, ro, ridx, qb, qo, 15, 3, 1)
+    # odd shapes: few rows / many strips, strip counts around multiples of the 4 warps
+    rng = random.Random(5)
+    refs, qs = [], []
+    for M, N in [(40, 5000), (3000, 257), (1500, 1300), (700, 1025), (2049, 2049), (257, 4097), (5000, 300)]:
+        a = "".join(rng.choice("ACGT") for _ in range(M))
+        b = list((a * (N // M + 2))[:N])
+        for _ in range(N // 15):
+            b[rng.randrange(N)] = rng.choice("ACGTN")
+        refs.append(a)
+        qs.append("".join(b))
+    rb, ro = packing.pack(refs)
+    qb, qo = packing.pack(qs)
+    _check_packed(gpu_aligner, oracle_port, 0, rb, ro, None, qb, qo, 15, 3, 1)
 
 
 def test_gpu_random_fuzz_batch(gpu_aligner, oracle_port, forced_path):
