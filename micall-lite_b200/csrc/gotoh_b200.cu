@@ -729,11 +729,13 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
             if (L.x2) rc = launch_forward<Vec16, false>(pl, fp, L.K, L.task_count);
             else if (!L.multi_strip) rc = launch_forward<Vec32, false>(pl, fp, L.K, L.task_count);
             else {
-                // K2: with fewer long pairs than resident warps a CTA per pair (4 warps pipelined over
-                // adjacent strips) keeps the SMs full; with plenty of pairs one warp per pair has no
-                // synchronisation at all.  GOTOH_B200_LONG=cta|warp pins the choice (tests).
+                // K2: with few long pairs a CTA per pair (4 warps pipelined over adjacent strips) keeps
+                // the SMs busy and cuts single-pair latency ~3x; with many pairs one warp per pair needs
+                // no synchronisation and wins (measured on B200, 9.6 kb pairs: 2000 pairs 857 vs 1225
+                // GCUPS; below ~2 pairs per resident CTA the CTA form is ahead).  GOTOH_B200_LONG=cta|warp
+                // pins the choice (tests, benchmarks).
                 const char* pin = getenv("GOTOH_B200_LONG");
-                bool cta = L.task_count < ws->sm_count * GOTOH_MIN_CTAS * FWD_WARPS;
+                bool cta = L.task_count < ws->sm_count * GOTOH_MIN_CTAS * 2;
                 if (pin) cta = (pin[0] == 'c');
                 rc = cta ? launch_forward_cta(pl, fp, L.task_count) : -1;
                 if (rc == -1) rc = launch_forward_k<Vec32, 8, true>(pl, fp, L.task_count);
