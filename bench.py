@@ -164,6 +164,9 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1 and "GOTOH_B200_HOST_THREADS" not in os.environ:
+        # ranks share the host: give each rank's packing threads its share of the cores
+        os.environ["GOTOH_B200_HOST_THREADS"] = str(max(2, (os.cpu_count() or 8) // world))
     al = Aligner()
     n = args.pairs
     ref, qb, qo = workloads.c2_reads_packed(n, seed=20260101 + rank)
