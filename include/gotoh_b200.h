@@ -48,7 +48,9 @@ enum {
     GOTOH_B200_ERANGE = -5,    /* output stride < M+N, lengths/penalties outside int32-safe range */
     GOTOH_B200_ENODEVICE = -6, /* no usable CUDA device / device index not present */
     GOTOH_B200_ECUDA = -7,     /* CUDA runtime error (message in gotoh_b200_last_error) */
-    GOTOH_B200_ENOMEM = -8     /* host or device allocation failed */
+    GOTOH_B200_ENOMEM = -8,    /* host or device allocation failed */
+    GOTOH_B200_ETRACEBACK = -9 /* gotoh2 only: no a/b/c bit set on the path, "Traceback failed, try local
+                                  alignment" (_gotoh2.c:403-407,601-603); that pair's score is INT32_MIN */
 };
 
 /* Library / device info. */
@@ -127,6 +129,26 @@ void gotoh_b200_release_cache(void);
 /* Pinned (page-locked) host memory for callers that want full-rate H2D/D2H copies. */
 void* gotoh_b200_host_alloc(int64_t bytes);
 void gotoh_b200_host_free(void* p);
+
+/*
+ * NEXT #1: the aligner the live pipeline calls, gotoh2.Aligner.align ->
+ * _gotoh2.align (micall/alignment/gotoh2.py:74-96, src/_gotoh2.c:442-607): Altschul-Erickson
+ * min-cost affine alignment, global or "local" (free end gaps), alphabet-indexed substitution
+ * matrix.  Pair k aligns seq1 = s1_bytes[s1_off[r]..s1_off[r+1]) (r = s1_idx ? s1_idx[k] : k)
+ * with seq2 = s2_bytes[s2_off[k]..s2_off[k+1]).  Bytes are cleaned like gotoh2.py:70-72 (ASCII
+ * upper-case, non-alphabet -> '?'); no trimming.  alphabet: NUL-terminated, <= 32 letters;
+ * matrix: l*l scores, row-major in alphabet order (gotoh2.py:47-64).  Outputs as in
+ * gotoh_b200_align_batch (the aligned strings contain the CLEANED characters, like the reference).
+ * Returns GOTOH_B200_ETRACEBACK if some pair's traceback fails (its out_score is INT32_MIN, its
+ * out_len 0; all other pairs are valid).
+ */
+int32_t gotoh_b200_gotoh2_align_batch(const uint8_t* s1_bytes, const int64_t* s1_off, int64_t n_s1,
+                                      const int32_t* s1_idx,
+                                      const uint8_t* s2_bytes, const int64_t* s2_off, int64_t n_pairs,
+                                      int32_t gop, int32_t gep, int32_t is_global,
+                                      const char* alphabet, const int32_t* matrix,
+                                      uint8_t* out1, uint8_t* out2, const int64_t* out_off,
+                                      int32_t* out_len, int32_t* out_score, int32_t device);
 
 /* Integer-issue microbenchmark used for the roofline denominator ("peak
  * INT32 issue must be measured").  Runs `which` (0 IADD3, 1 VIMNMX, 2 VIADDMNMX,

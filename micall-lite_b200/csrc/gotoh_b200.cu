@@ -12,6 +12,7 @@
 #include "gotoh_intpeak.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1008,6 +1009,8 @@ extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_
         if (rcs[d]) return fail(rcs[d], "device %d: %s", devs[d], msgs[d].c_str());
     return GOTOH_B200_OK;
 }
+
+#include "gotoh2_host.cuh"
 
 extern "C" int32_t gotoh_b200_int_peak(int32_t device, int32_t which, double* ginstr_per_s) {
     if (!ginstr_per_s) return fail(GOTOH_B200_EINVAL, "NULL argument");

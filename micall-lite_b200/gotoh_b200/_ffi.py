@@ -11,7 +11,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(os.path.dirname(_PKG), "lib", "libgotoh_b200.so")
 
-OK, EINVAL, EEMPTY, EDOMAIN, ESENTINEL, ERANGE, ENODEVICE, ECUDA, ENOMEM = 0, -1, -2, -3, -4, -5, -6, -7, -8
+OK, EINVAL, EEMPTY, EDOMAIN, ESENTINEL, ERANGE, ENODEVICE, ECUDA, ENOMEM, ETRACEBACK = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
 NT, HIV25, AA_RB = 0, 1, 2
 
 # every symbol include/gotoh_b200.h declares (tests check the library exports all of them)
@@ -20,7 +20,7 @@ SYMBOLS = (
     "gotoh_b200_pairscore_table", "gotoh_b200_align_batch", "gotoh_b200_plan_create",
     "gotoh_b200_plan_run", "gotoh_b200_plan_fetch", "gotoh_b200_plan_destroy",
     "gotoh_b200_plan_stat", "gotoh_b200_host_alloc", "gotoh_b200_host_free", "gotoh_b200_int_peak",
-    "gotoh_b200_release_cache",
+    "gotoh_b200_release_cache", "gotoh_b200_gotoh2_align_batch",
 )
 
 
@@ -68,6 +68,9 @@ class Library:
         lib.gotoh_b200_host_alloc.argtypes = [_i64]
         lib.gotoh_b200_host_free.restype = None
         lib.gotoh_b200_host_free.argtypes = [_vp]
+        lib.gotoh_b200_gotoh2_align_batch.restype = _i32
+        lib.gotoh_b200_gotoh2_align_batch.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
+                                                      ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp, _i32]
         lib.gotoh_b200_release_cache.restype = None
         lib.gotoh_b200_release_cache.argtypes = []
         lib.gotoh_b200_int_peak.restype = _i32
