@@ -150,6 +150,12 @@ int32_t gotoh_b200_gotoh2_align_batch(const uint8_t* s1_bytes, const int64_t* s1
                                       uint8_t* out1, uint8_t* out2, const int64_t* out_off,
                                       int32_t* out_len, int32_t* out_score, int32_t device);
 
+/* Statistics of the calling thread's last gotoh_b200_gotoh2_align_batch (benchmarks, tests): fills up to
+ * n <= 10 doubles and returns how many: 0 grid cells sum (l1+1)(l2+1), 1 device ms of all kernels (CUDA
+ * events), 2 forward ms, 3 reverse-sweep ms, 4 walk+emit ms, 5 kernel launches, 6 tie-bit arena bytes,
+ * 7 arena chunks, 8 bytes copied H2D, 9 bytes copied D2H. */
+int32_t gotoh_b200_gotoh2_last_stats(double* out, int32_t n);
+
 /* Integer-issue microbenchmark used for the roofline denominator ("peak
  * INT32 issue must be measured").  Runs `which` (0 IADD3, 1 VIMNMX, 2 VIADDMNMX,
  * 3 VIADDMNMX.S16x2, 4 VIMNMX3, 5 IMAD, 6 LOP3, 7 mixed ALU+IMAD, 8 forward-DP cell mix)

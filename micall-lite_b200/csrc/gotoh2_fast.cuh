@@ -1,0 +1,541 @@
+// gotoh2_fast.cuh - tuned sm_100a kernels for MiCall-Lite's LIVE aligner `_gotoh2.align`
+// (SURVEY.md 8f "next" #1; reference micall/alignment/src/_gotoh2.c, driven by gotoh2.py:74-96 from
+// core/remap.py:248 and core/aln2counts.py:187).  Used whenever gop >= 0 and gep >= 0 (every caller in the
+// reference); gotoh2_kernels.cuh keeps the general kernels for exotic penalties.
+//
+//   k2f<K,MULTI,BITS>  cost_assignment (_gotoh2.c:137-201).  One warp per STRIP TASK (pair, strip of 32*K
+//        columns); lane l owns K columns and is one row behind lane l-1.  Costs live in the frame
+//        X~(i,j) = X(i,j) - (i+j)*u, which removes the "+u" of both gap recurrences (:156,:166):
+//            q~ = min(q~left, R~left + v)   p~ = min(p~up, R~up + v)   R~ = min(R~diag - d - 2u, p~, q~)
+//        = 2 VIADDMNMX + 1 add + 1 VIMNMX3.  The seven tie bits of a cell (:157-176 d,e,f,g; :190-198 a,b,c)
+//        come from saturating differences instead of compare+select:
+//            code_DE = clamp(p~up - (R~up+v) + 1, 0, 2)     one VIADDMNMX.RELU   (0: d  1: d,e  2: e)
+//            code_FG = clamp(q~left - (R~left+v) + 1, 0, 2) one VIADDMNMX.RELU
+//            not_a   = min(p~ - R~, 1), not_b, not_c        one VIADDMNMX each
+//        and are packed by multiply-add chains on the FMA pipe.  BITS=false is the score-only form (no tie bits,
+//        no arena) used for the edit distance of remap.py:250.
+//        Strips of one pair run CONCURRENTLY on different warps (any CTA): strip s publishes its last column
+//        (R~, q~) to global memory every 32 rows and strip s+1 follows it ~64 rows behind - an anti-diagonal
+//        wavefront across the whole grid.  Tasks are claimed from an atomic counter in (pair, strip) order, so
+//        a strip's producer is always claimed earlier and is running: the spin-waits cannot deadlock.
+//   k2r<K,MULTI>       edge_assignment, Altschul-Erickson steps 8-11 (_gotoh2.c:205-312), the exact time
+//        reversal of k2f, bit-parallel over the K columns of a lane: the b-chain along a row
+//        fin_b[j] = G[j] | (P[j] & fin_b[j+1]) is a carry chain and is resolved by ONE integer addition.
+//   k2f_walk           traceback with priority a > b > c (_gotoh2.c:374-408) into the op script k_emit consumes.
+#pragma once
+
+#include "gotoh_kernels.cuh"
+
+namespace gotoh {
+namespace g2f {
+
+enum { INF = 1 << 29, BIGE = 1 << 28, FSTEPS = 4, PUB = 32 };
+
+struct StripTask {
+    int32_t pair;
+    int32_t strip;
+};
+
+struct Extra {              // per pair, beside PairInfo
+    int64_t bnd_off;        // first boundary-column entry of this pair: [(nstrips-1)][M+2]
+    int32_t slot0;          // first (pair, strip) slot: progress counters, last-row partials
+    int32_t nstrips;
+};
+
+struct Params {
+    const PairInfo* pairs;      // M = l1, N = l2, dir_off = first uint4 of the pair in BOTH planes, nblk = blocks per strip
+    const Extra* extra;
+    const StripTask* tasks;     // (pair, strip) in pair-major, strip-ascending order
+    int32_t task_count;
+    const uint8_t* s1_idx;      // alphabet indices of seq1, REF_PAD zero bytes on both sides of every sequence
+    const uint8_t* s2_idx;
+    const int32_t* dmat;        // l*l substitution scores (gotoh2.py:47-64)
+    int32_t l, v, u, is_global; // v = gap open, u = gap extend (_gotoh2.c:31-32)
+    uint32_t two, four;         // == 2, 4 at run time; opaque so acc*two+x stays an IMAD (FMA pipe)
+    uint4* lo;                  // plane 0: code_DE | code_FG << 16, one word per lane-step
+    uint4* hi;                  // plane 1: a | b << 8 | c << 16 (k2f: forward bits, k2r: final bits)
+    int2* bnd;                  // forward strip boundaries (R~, q~) per row
+    uint8_t* rbnd;              // reverse strip boundaries: F | G<<1 | fin_b<<2 | fin_c<<3 of a strip's first column
+    int32_t* prog_f;            // rows published per (pair, strip): forward counts up from 0 ...
+    int32_t* prog_r;            // ... reverse counts DOWN from M+1 (stored as rows still missing)
+    int32_t* part_min;          // last-row partial minimum per (pair, strip)
+    int32_t* part_j;
+    int32_t* best;              // R at the start cell (score = -best)
+    int32_t* start_i;
+    int32_t* start_j;
+    uint32_t* counter_f;        // task schedulers
+    uint32_t* counter_r;
+};
+
+__device__ __forceinline__ int ld_volatile(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+__device__ __forceinline__ void st_volatile(int32_t* p, int v) { *reinterpret_cast<volatile int32_t*>(p) = v; }
+
+#ifdef GOTOH_SIMT_EMU
+template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return *p; }
+#else
+template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
+#endif
+
+template <int K>
+struct Smem {
+    enum { K4 = (K + 3) / 4 };
+    static __host__ __device__ size_t per_warp(int l) { return (size_t)l * K4 * 32 * 16 + 2 * 32 * sizeof(int2); }
+};
+
+// -------------------------------------------------------------------------------------------------------
+// forward
+// -------------------------------------------------------------------------------------------------------
+template <int K, bool MULTI, bool BITS>
+struct Fwd {
+    enum { K4 = (K + 3) / 4, KMASK = (1 << K) - 1 };
+    int lane, M, N, j0, strip, u, v, c1v, c2v;
+    bool last_strip;
+    unsigned two, four, keep;
+    int injq, c0run, c0step;
+    unsigned CA3;                  // (KMASK + off_K) * 0x010101
+    const uint4* prof_lane;
+    const uint8_t* cls;
+    int2* ring;
+    const int2* bnd_in;
+    int2* bnd_out;
+    int vq[K];
+    int R[K], P[K], nRu[K];
+    int sendR, sendQ, Rd_in, next_cls;
+    int bf, best_i;                // last column: running minimum in the frame of the current row, and its row
+    int row_min, row_j, r_ll;      // last row candidates of this lane (unframed)
+    uint4 wlo, whi;
+
+    // row 0: R(0,j) = v + j*u (global) or 0 (local), p(0,j) = +inf (_gotoh2.c:96-116); padding columns clone column N
+    __device__ __forceinline__ int row0(int j, int is_global) const { return j == 0 ? 0 : (is_global ? v : -j * u); }
+    __device__ __forceinline__ void row0_init(int is_global) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            R[k] = row0(min(j0 + k + 1, N), is_global);
+            P[k] = INF;
+            nRu[k] = c1v - R[k];
+        }
+        Rd_in = row0(min(j0, N), is_global);
+        bf = row0(N, is_global);
+        best_i = 0;
+    }
+
+    template <bool SLOW>
+    __device__ __forceinline__ void step(const int t, const int s, const int is_global) {
+        const int i = t - lane;
+        const int my_cls = next_cls;
+        next_cls = cls[i];
+        int Rl = __shfl_up_sync(0xffffffffu, sendR, 1);
+        int Ql = __shfl_up_sync(0xffffffffu, sendQ, 1);
+        int rdiag = Rd_in;
+        if (MULTI && strip > 0) {
+            if (((t - 1) & 31) == 0) {
+                __syncwarp();
+                const int row = t + lane;
+                int2 b = make_int2(0, 0);
+                if (row >= 1 && row <= M) b = ld_cg(&bnd_in[row]);
+                ring[(((t - 1) >> 5) & 1) * 32 + lane] = b;
+                __syncwarp();
+            }
+            if (lane == 0) {
+                const int2 b = ring[(((t - 1) >> 5) & 1) * 32 + ((t - 1) & 31)];
+                Rl = b.x; Ql = b.y;
+            }
+        } else {
+            // column 0 (_gotoh2.c:101-116): R~(i,0) = v (global) or -i*u (local), q(i,0) = +inf, injected into lane 0
+            c0run += c0step;
+            Rl = (int)((unsigned)Rl * keep + (unsigned)c0run);
+            Ql = (int)((unsigned)Ql * keep + (unsigned)injq);
+        }
+        Rd_in = Rl;
+
+        const uint4* prow = prof_lane + my_cls * (K4 * 32);
+        int Rleft = Rl, nRleft = c1v - Rl, q = Ql;
+        unsigned accDE = 0, accFG = 0, accA = 0, accB = 0, accC = 0;
+#pragma unroll
+        for (int kq = 0; kq < K4; ++kq) {
+            const uint4 e4 = prow[kq * 32];
+            const int ev[4] = {(int)e4.x, (int)e4.y, (int)e4.z, (int)e4.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = kq * 4 + kk;
+                if (k < K) {
+                    if (BITS) {
+                        const int cFG = __viaddmin_s32_relu(q, nRleft, 2);       // f,g of this cell (_gotoh2.c:167-173)
+                        const int cDE = __viaddmin_s32_relu(P[k], nRu[k], 2);    // d,e of this cell (_gotoh2.c:157-163)
+                        accFG = accFG * four + (unsigned)cFG;
+                        accDE = accDE * four + (unsigned)cDE;
+                    }
+                    q = __viaddmin_s32(Rleft, vq[k], q);                          // _gotoh2.c:166
+                    const int p = __viaddmin_s32(R[k], v, P[k]);                  // _gotoh2.c:156
+                    const int dg = rdiag + ev[kk];                                // _gotoh2.c:185
+                    const int r = __vimin3_s32(dg, p, q);                         // _gotoh2.c:186-187
+                    const int nr = c1v - r;
+                    if (BITS) {
+                        accA = accA * two + (unsigned)__viaddmin_s32(p, nr, c2v);   // (1-v) + [R != p]   (_gotoh2.c:190-192)
+                        accB = accB * two + (unsigned)__viaddmin_s32(q, nr, c2v);   // (1-v) + [R != q]   (:193-195)
+                        accC = accC * two + (unsigned)__viaddmin_s32(dg, nr, c2v);  // (1-v) + [R != diag] (:196-198)
+                    }
+                    rdiag = R[k];
+                    R[k] = r; P[k] = p; nRu[k] = nr;
+                    Rleft = r; nRleft = nr;
+                }
+            }
+        }
+        sendR = R[K - 1];
+        sendQ = q;
+        if (BITS) {
+            const unsigned wl = accFG * 65536u + accDE;
+            const unsigned wh = CA3 - (accA + accB * 256u + accC * 65536u);
+            if (s == 0) { wlo.x = wl; whi.x = wh; } else if (s == 1) { wlo.y = wl; whi.y = wh; }
+            else if (s == 2) { wlo.z = wl; whi.z = wh; } else { wlo.w = wl; whi.w = wh; }
+        }
+        // last column: first strict minimum scanning top-down (_gotoh2.c:330-339), in the frame of the current row
+        if (!MULTI || last_strip) {
+            bf -= u;
+            if (!SLOW || (i >= 1 && i <= M)) {
+                if (R[K - 1] < bf) { bf = R[K - 1]; best_i = i; }
+            }
+        }
+        if (MULTI && !last_strip && lane == 31 && i >= 1 && i <= M) bnd_out[i] = make_int2(R[K - 1], q);
+        if (SLOW) {
+            if (i == 0) row0_init(is_global);
+            if (i == M) {
+                // bottom row: first strict minimum left to right (_gotoh2.c:341-350), unframed
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int j = j0 + k + 1;
+                    const int val = R[k] + (M + j) * u;
+                    if (j <= N && val < row_min) { row_min = val; row_j = j; }
+                }
+                r_ll = R[K - 1] + (M + N) * u;          // owner lane of column N: R(l1, l2)
+            }
+        }
+    }
+};
+
+template <int K, bool MULTI, bool BITS>
+__global__ void __launch_bounds__(128, 4) k2f(const Params p) {
+    typedef Fwd<K, MULTI, BITS> W;
+    enum { K4 = W::K4 };
+    GOTOH_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* my_smem = smem_raw + (size_t)warp * Smem<K>::per_warp(p.l);
+    uint4* prof = reinterpret_cast<uint4*>(my_smem);
+    W w;
+    w.lane = lane;
+    w.u = p.u; w.v = p.v;
+    w.c1v = 1 - p.v; w.c2v = 2 - p.v;
+    w.two = p.two; w.four = p.four;
+    w.prof_lane = prof + lane;
+    w.ring = reinterpret_cast<int2*>(my_smem + (size_t)p.l * K4 * 32 * 16);
+    w.CA3 = (unsigned)(W::KMASK + (1 - p.v) * W::KMASK) * 0x010101u;
+    const int e_pad = BIGE;
+
+    for (;;) {
+        unsigned tsk = 0;
+        if (lane == 0) tsk = atomicAdd(p.counter_f, 1u);
+        tsk = __shfl_sync(0xffffffffu, tsk, 0);
+        if (tsk >= (unsigned)p.task_count) break;
+        const StripTask task = p.tasks[tsk];
+        const PairInfo pr = p.pairs[task.pair];
+        const Extra ex = p.extra[task.pair];
+        const int M = pr.M, N = pr.N, strip = task.strip, nstrips = ex.nstrips, nblk = pr.nblk;
+        const uint8_t* s2 = p.s2_idx + pr.qry_pos;
+        const int j0 = (strip * 32 + lane) * K;
+        w.M = M; w.N = N; w.strip = strip; w.j0 = j0;
+        w.last_strip = (strip == nstrips - 1);
+        w.cls = p.s1_idx + pr.ref_pos;
+        w.row_min = 2147483647; w.row_j = 0; w.r_ll = 0;
+        if (MULTI) {
+            w.bnd_in = p.bnd + ex.bnd_off + (int64_t)(strip - 1) * (M + 2);
+            w.bnd_out = p.bnd + ex.bnd_off + (int64_t)strip * (M + 2);
+        }
+        const bool col0 = (!MULTI || strip == 0);
+        w.keep = (p.two >> 1) - ((lane == 0 && col0) ? 1u : 0u);
+        w.injq = (lane == 0 && col0) ? INF : 0;
+        w.c0run = (lane == 0 && col0 && p.is_global) ? p.v : 0;
+        w.c0step = (lane == 0 && col0 && !p.is_global) ? -p.u : 0;
+
+        // ---- query profile of this strip: prof[class][k/4][lane] = -d[class][b_j] - 2u; padding columns never win
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) w.vq[k] = (j0 + k) < N ? p.v : 0;
+        for (int c = 0; c < p.l; ++c) {
+            const int32_t* drow = p.dmat + c * p.l;
+#pragma unroll
+            for (int kq = 0; kq < K4; ++kq) {
+                unsigned e[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = kq * 4 + kk, ja = j0 + k;
+                    int ea = e_pad;
+                    if (k < K && ja < N) ea = -drow[s2[ja]] - 2 * p.u;
+                    e[kk] = (unsigned)ea;
+                }
+                prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
+            }
+        }
+        __syncwarp();
+        w.sendR = 0; w.sendQ = 0;
+        w.wlo = make_uint4(0, 0, 0, 0); w.whi = make_uint4(0, 0, 0, 0);
+        w.row0_init(p.is_global);
+        w.next_cls = w.cls[-lane];
+
+        int32_t* prog_in = p.prog_f + ex.slot0 + strip - 1;
+        int32_t* prog_out = p.prog_f + ex.slot0 + strip;
+        uint4* dlo = BITS ? p.lo + pr.dir_off + (int64_t)strip * nblk * 32 + lane : nullptr;
+        uint4* dhi = BITS ? p.hi + pr.dir_off + (int64_t)strip * nblk * 32 + lane : nullptr;
+        for (int tb = 0; tb < nblk; ++tb) {
+            const int t0 = tb * FSTEPS + 1, hi = t0 + FSTEPS - 1;
+            if (MULTI && strip > 0 && ((t0 - 1) & 31) == 0) {
+                // lane 0 consumes rows t0 .. t0+31 of the left strip's last column during the next 32 steps
+                if (lane == 0) {
+                    const int need = min(t0 + 31, M);
+                    while (ld_volatile(prog_in) < need) gotoh_pause();
+                }
+                __syncwarp();
+            }
+            const bool slow = (t0 <= 31) || (hi >= M);
+            if (slow) {
+#pragma unroll
+                for (int s = 0; s < FSTEPS; ++s) w.template step<true>(t0 + s, s, p.is_global);
+            } else {
+#pragma unroll
+                for (int s = 0; s < FSTEPS; ++s) w.template step<false>(t0 + s, s, p.is_global);
+            }
+            if (BITS) { dlo[(int64_t)tb * 32] = w.wlo; dhi[(int64_t)tb * 32] = w.whi; }
+            if (MULTI && !w.last_strip && ((hi & (PUB - 1)) == 0) && hi - 31 >= 1 && hi - 31 < M) {
+                __syncwarp();
+                if (lane == 31) { __threadfence(); st_volatile(prog_out, hi - 31); }
+            }
+        }
+
+        // ---- bottom-row partial of this strip (smallest j wins ties), then the final publish ------------
+        int row_min = w.row_min, row_j = w.row_j;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int om = __shfl_xor_sync(0xffffffffu, row_min, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, row_j, off);
+            if (om < row_min || (om == row_min && oj < row_j)) { row_min = om; row_j = oj; }
+        }
+        if (MULTI && !w.last_strip) {
+            if (lane == 0) { p.part_min[ex.slot0 + strip] = row_min; p.part_j[ex.slot0 + strip] = row_j; }
+            __syncwarp();
+            if (lane == 31) { __threadfence(); st_volatile(prog_out, M); }
+            continue;
+        }
+        // ---- last strip: start cell (_gotoh2.c:327-352) ---------------------------------------------------
+        const int owner = ((N - 1) / K) & 31;
+        const int i_fin = nblk * FSTEPS - lane;
+        int col_min = w.bf + (i_fin + N) * p.u;            // unframed
+        col_min = __shfl_sync(0xffffffffu, col_min, owner);
+        const int col_i = __shfl_sync(0xffffffffu, w.best_i, owner);
+        const int r_ll = __shfl_sync(0xffffffffu, w.r_ll, owner);
+        if (lane == 0) {
+            int best = r_ll, bi = M, bj = N;
+            if (!p.is_global) {
+                if (col_min < best) { best = col_min; bi = col_i; bj = N; }
+                int rm = 0, rj = 0;                          // R(l1, 0) = 0 in local mode (_gotoh2.c:111)
+                if (MULTI) {
+                    for (int s = 0; s < nstrips - 1; ++s) {
+                        const int pm = ld_cg(&p.part_min[ex.slot0 + s]), pj = ld_cg(&p.part_j[ex.slot0 + s]);
+                        if (pm < rm) { rm = pm; rj = pj; }
+                    }
+                }
+                if (row_min < rm) { rm = row_min; rj = row_j; }
+                if (rm < best) { best = rm; bi = M; bj = rj; }
+            }
+            p.best[task.pair] = best;
+            p.start_i[task.pair] = bi;
+            p.start_j[task.pair] = bj;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// reverse sweep
+// -------------------------------------------------------------------------------------------------------
+// even bits of each 16-bit half -> the low 8 bits of that half
+__device__ __forceinline__ unsigned compress_even(unsigned x) {
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    return x;
+}
+
+template <int K, bool MULTI>
+__global__ void __launch_bounds__(128, 4) k2r(const Params p) {
+    enum { KMASK = (1 << K) - 1 };
+    __shared__ uint8_t s_ring[4][2][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned local = p.is_global ? 0u : 1u;
+
+    for (;;) {
+        unsigned tsk = 0;
+        if (lane == 0) tsk = atomicAdd(p.counter_r, 1u);
+        tsk = __shfl_sync(0xffffffffu, tsk, 0);
+        if (tsk >= (unsigned)p.task_count) break;
+        const StripTask task = p.tasks[p.task_count - 1 - (int)tsk];      // (pair, strip) in strip-DEscending order
+        const PairInfo pr = p.pairs[task.pair];
+        const Extra ex = p.extra[task.pair];
+        const int M = pr.M, N = pr.N, strip = task.strip, nstrips = ex.nstrips, nblk = pr.nblk;
+        const int j0 = (strip * 32 + lane) * K;
+        const bool last_strip = (strip == nstrips - 1);
+        // columns j0+1 .. j0+K, column k at bit K-1-k; real columns are j <= N
+        const int nreal = max(0, min(K, N - j0));
+        const unsigned colmask = (unsigned)(KMASK & ~((1 << (K - nreal)) - 1));
+        const unsigned bitN = (N > j0 && N <= j0 + K) ? (1u << (K - 1 - (N - j0 - 1))) : 0u;
+        const unsigned sent_last = local ? colmask : bitN;      // c of the sentinel row below row M (_gotoh2.c:118-133)
+        const unsigned sent_rows = local ? bitN : 0u;           // c of the sentinel column right of column N
+        const uint8_t* rb_in = p.rbnd + ex.bnd_off + (int64_t)strip * (M + 2);         // written by strip+1
+        uint8_t* rb_out = p.rbnd + ex.bnd_off + (int64_t)(strip - 1) * (M + 2);        // read by strip-1
+        int32_t* prog_in = p.prog_r + ex.slot0 + strip + 1;
+        int32_t* prog_out = p.prog_r + ex.slot0 + strip;
+        uint8_t* ring = &s_ring[warp][0][0];
+
+        unsigned finA_dn = 0, finC_dn = 0, D_dn = 0, E_dn = 0;   // row below (this lane's previous step)
+        unsigned send = 0;                                        // what lane-1 needs next step
+        unsigned finC_top_prev = 0;                               // fin_c of my first column, one row below the row in `send`
+        unsigned in_c_prev = 0;                                   // MULTI lane 31: fin_c of the right strip's first column, row below
+        const uint4* slo = p.lo + pr.dir_off + (int64_t)strip * nblk * 32 + lane;
+        uint4* shi = p.hi + pr.dir_off + (int64_t)strip * nblk * 32 + lane;
+        __syncwarp();
+        for (int tb = nblk - 1; tb >= 0; --tb) {
+            const int t0 = tb * FSTEPS + 1, thi = t0 + FSTEPS - 1;
+            if (MULTI && !last_strip && ((thi & 31) == 0 || tb == nblk - 1)) {
+                // lane 31 consumes rows thi-31 down to (thi&~31)+1-31... stage the 32 rows of this window:
+                // window index wdw = (thi-1)>>5 covers steps 32*wdw+1 .. 32*wdw+32, i.e. lane-31 rows 32*wdw-30 .. 32*wdw+1
+                const int wdw = (thi - 1) >> 5;
+                const int lowrow = 32 * wdw - 30;
+                if (lane == 0) {
+                    const int need = max(lowrow, 1);          // rows >= need must be published (counts down)
+                    while (ld_volatile(prog_in) > need) gotoh_pause();
+                }
+                __syncwarp();
+                const int row = lowrow + lane;
+                uint8_t b = 0;
+                if (row >= 1 && row <= M) b = ld_cg(&rb_in[row]);
+                ring[(wdw & 1) * 32 + lane] = b;
+                __syncwarp();
+            }
+            const uint4 l4 = slo[(int64_t)tb * 32];
+            uint4 h4 = shi[(int64_t)tb * 32];
+#pragma unroll
+            for (int s = FSTEPS - 1; s >= 0; --s) {
+                const int t = t0 + s, i = t - lane;
+                const unsigned wl = s == 0 ? l4.x : s == 1 ? l4.y : s == 2 ? l4.z : l4.w;
+                const unsigned wh = s == 0 ? h4.x : s == 1 ? h4.y : s == 2 ? h4.z : h4.w;
+                const bool valid = (i >= 1 && i <= M);
+                const unsigned m8 = valid ? colmask : 0u;
+                // forward bits of this row
+                const unsigned even = wl & 0x55555555u, odd = (wl >> 1) & 0x55555555u;
+                const unsigned eg = compress_even(even | odd);            // e | g<<16
+                const unsigned df = compress_even(~odd & 0x55555555u);    // d | f<<16
+                const unsigned D = df & m8, E = eg & m8, F = (df >> 16) & m8, G = (eg >> 16) & m8;
+                const unsigned ownA = wh & m8, ownB = (wh >> 8) & m8, ownC = (wh >> 16) & m8;
+                // right neighbour column (lane+1 processed this row in its previous step)
+                unsigned in = __shfl_down_sync(0xffffffffu, send, 1);
+                if (lane == 31) {
+                    in = 0;
+                    if (MULTI && !last_strip && valid) {
+                        const int wdw = (t - 1) >> 5;
+                        const unsigned x = ring[(wdw & 1) * 32 + (i - (32 * wdw - 30))];
+                        in = (x & 7u) | (in_c_prev << 3);
+                        in_c_prev = (x >> 3) & 1u;
+                    }
+                }
+                const unsigned Fr = ((F << 1) | (in & 1u)) & KMASK;
+                const unsigned Gr = ((G << 1) | ((in >> 1) & 1u)) & KMASK;
+                const unsigned cin = (in >> 2) & 1u;
+                unsigned C1 = ((finC_dn << 1) | ((in >> 3) & 1u)) & KMASK;
+                C1 |= (i == M) ? sent_last : sent_rows;
+                C1 &= m8;
+                const unsigned A1 = finA_dn;
+                const unsigned K0 = (A1 & E_dn) | C1;
+                const unsigned Gg = ownB & K0, Pp = (ownB & Gr) | Fr;
+                const unsigned x = Gg | Pp, y = Gg;
+                const unsigned cvec = (x + y + cin) ^ x ^ y;             // bit b: fin_b of the column right of bit b
+                const unsigned B1 = cvec & KMASK;
+                const unsigned finB = (cvec >> 1) & m8;
+                const unsigned keepm = K0 | (B1 & Gr);                    // step 8 (_gotoh2.c:237-242)
+                const unsigned finA = ((ownA & keepm) | (A1 & D_dn)) & m8; // step 10 (:251-270)
+                const unsigned finC = ownC & keepm;
+                const unsigned nh = finA | (finB << 8) | (finC << 16);
+                if (s == 0) h4.x = nh; else if (s == 1) h4.y = nh; else if (s == 2) h4.z = nh; else h4.w = nh;
+                // hand-over to the left lane: F, G, fin_b of my first column at this row; fin_c of it one row below
+                const unsigned top = K - 1;
+                send = ((F >> top) & 1u) | (((G >> top) & 1u) << 1) | (((finB >> top) & 1u) << 2) | (finC_top_prev << 3);
+                if (MULTI && strip > 0 && lane == 0 && valid)
+                    rb_out[i] = (uint8_t)(((F >> top) & 1u) | (((G >> top) & 1u) << 1) | (((finB >> top) & 1u) << 2) | (((finC >> top) & 1u) << 3));
+                finC_top_prev = (finC >> top) & 1u;
+                finA_dn = finA; finC_dn = finC; D_dn = D; E_dn = E;
+            }
+            shi[(int64_t)tb * 32] = h4;
+            if (MULTI && strip > 0 && ((t0 - 1) & (PUB - 1)) == 0 && t0 > 1 && t0 <= M) {
+                // lane 0 has finished rows >= t0
+                __syncwarp();
+                if (lane == 0) { __threadfence(); st_volatile(prog_out, t0); }
+            }
+        }
+        if (MULTI && strip > 0) {
+            __syncwarp();
+            if (lane == 0) { __threadfence(); st_volatile(prog_out, 0); }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// traceback
+// -------------------------------------------------------------------------------------------------------
+struct WalkParams {
+    const PairInfo* pairs;
+    int32_t pair_first, pair_count;
+    const uint32_t* hi;         // final a/b/c plane viewed as uint32
+    const int32_t* best;
+    const int32_t* start_i;
+    const int32_t* start_j;
+    uint32_t* ops;
+    int32_t* nops;
+    int32_t* i0;
+    int32_t* j0;
+    int32_t* out_len;
+    int32_t* score;             // -best, or INT_MIN when the traceback failed (_gotoh2.c:403-407)
+};
+
+__global__ void __launch_bounds__(128) k2f_walk(const WalkParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.pair_count) return;
+    const int pi = p.pair_first + idx;
+    const PairInfo pr = p.pairs[pi];
+    const int K = pr.K, nblk = pr.nblk;
+    int i = p.start_i[pi], j = p.start_j[pi];
+    const int right = (i == pr.M && j < pr.N) ? (pr.N - j) : (pr.M - i);
+    uint32_t* ops = p.ops + pr.ops_off;
+    uint32_t cur = 0;
+    int n = 0;
+    bool failed = false;
+    while (i > 0 && j > 0) {
+        const int jj = j - 1, strip = jj / (32 * K), rem = jj - strip * 32 * K, lane = rem / K, k = rem - lane * K;
+        const int tt = i + lane - 1, tb = tt >> 2, s = tt & 3;
+        const uint32_t w = p.hi[((pr.dir_off + ((int64_t)strip * nblk + tb) * 32 + lane) << 2) + s];
+        const int bit = K - 1 - k;
+        uint32_t d;
+        if ((w >> bit) & 1u) { d = DIR_UP; --i; }                         // vertical first (_gotoh2.c:381-388)
+        else if ((w >> (8 + bit)) & 1u) { d = DIR_LEFT; --j; }            // then horizontal (:389-395)
+        else if ((w >> (16 + bit)) & 1u) { d = DIR_DIAG; --i; --j; }      // then diagonal (:396-402)
+        else { failed = true; break; }                                    // "traceback failed" (:403-407)
+        cur |= d << (2 * (n & 15));
+        if ((n & 15) == 15) { ops[n >> 4] = cur; cur = 0; }
+        ++n;
+    }
+    if (n & 15) ops[n >> 4] = cur;
+    const int k = i > j ? i : j;
+    p.nops[pi] = n;
+    p.i0[pi] = failed ? 0 : i;
+    p.j0[pi] = failed ? 0 : j;
+    p.out_len[pi] = failed ? 0 : k + n + right;
+    p.score[pi] = failed ? (int)0x80000000 : -p.best[pi];
+}
+
+}  // namespace g2f
+}  // namespace gotoh

@@ -3,8 +3,306 @@
 #pragma once
 
 #include "gotoh2_kernels.cuh"
+#include "gotoh2_fast.cuh"
 
 namespace {
+
+// stats of this thread's last gotoh2 call (gotoh_b200_gotoh2_last_stats)
+thread_local double g2_stats[10] = {0};
+
+struct G2Events {
+    cudaEvent_t e[5] = {0, 0, 0, 0, 0};
+    bool ok = false;
+    bool create() {
+        for (auto& x : e) if (cudaEventCreate(&x) != cudaSuccess) return false;
+        return ok = true;
+    }
+    ~G2Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+};
+
+struct G2Bufs {
+    DevBuf<uint8_t> raw1, idx1, raw2, idx2, o1, o2, rbnd;
+    DevBuf<PairInfo> pairs;
+    DevBuf<int32_t> dmat, best, si, sj, nops, i0, j0, lenp, score, olen, oscore, prog, part;
+    DevBuf<uint32_t> ops, counters;
+    DevBuf<uint2> arena;
+    DevBuf<uint4> lo, hi;
+    DevBuf<int2> fbnd;
+    DevBuf<gotoh::g2f::Extra> extra;
+    DevBuf<gotoh::g2f::StripTask> tasks;
+    ~G2Bufs() {
+        raw1.release(); idx1.release(); raw2.release(); idx2.release(); o1.release(); o2.release(); rbnd.release();
+        pairs.release(); dmat.release(); best.release(); si.release(); sj.release(); nops.release(); i0.release();
+        j0.release(); lenp.release(); score.release(); olen.release(); oscore.release(); prog.release(); part.release();
+        ops.release(); counters.release(); arena.release(); lo.release(); hi.release(); fbnd.release();
+        extra.release(); tasks.release();
+    }
+};
+
+struct G2Run {
+    int64_t n = 0;
+    int l = 0, gop = 0, gep = 0, is_global = 0, sm_count = 1;
+    bool score_only = false;
+    int64_t max_rows = 0;
+    G2Events ev;
+    double ms_f = 0, ms_r = 0, ms_w = 0;
+    int launches = 0, chunks = 0;
+    int64_t arena_bytes = 0;
+};
+
+// k_emit + the per-chunk timing bookkeeping shared by both kernel families
+int g2_emit(G2Bufs& b, G2Run& run, int first, int count) {
+    EmitParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.pairs = b.pairs.p; ep.pair_first = first; ep.pair_count = count;
+    ep.ref_raw = b.raw1.p; ep.qry = b.raw2.p; ep.ops = b.ops.p; ep.nops = b.nops.p;
+    ep.i0 = b.i0.p; ep.j0 = b.j0.p; ep.end_i = b.si.p; ep.end_j = b.sj.p;
+    ep.out_len_plan = b.lenp.p; ep.score_plan = b.score.p;
+    ep.out_ref = b.o1.p; ep.out_qry = b.o2.p; ep.out_len = b.olen.p; ep.out_score = b.oscore.p;
+    GOTOH_LAUNCH(k_emit, dim3((count + 3) / 4), dim3(128), 0, (cudaStream_t)0, ep);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(run.ev.e[3], 0));
+    CU(cudaEventSynchronize(run.ev.e[3]));
+    float a = 0, bb = 0, c = 0;
+    CU(cudaEventElapsedTime(&a, run.ev.e[0], run.ev.e[1]));
+    CU(cudaEventElapsedTime(&bb, run.ev.e[1], run.ev.e[2]));
+    CU(cudaEventElapsedTime(&c, run.ev.e[2], run.ev.e[3]));
+    run.ms_f += a; run.ms_r += bb; run.ms_w += c;
+    run.launches += 2;
+    return 0;
+}
+
+// ---- general kernels (gotoh2_kernels.cuh): any penalties, one warp per pair -------------------------------
+int g2_run_general(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
+    using namespace gotoh::g2;
+    const size_t n = (size_t)run.n;
+    const int grid = run.sm_count * 4, nwarps = grid * 4;
+    const int64_t bstride = (run.max_rows + 2 + 15) & ~15LL;
+    CU(b.fbnd.ensure((size_t)(nwarps * bstride)));
+    CU(b.rbnd.ensure((size_t)(nwarps * bstride)));
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    int64_t budget = (int64_t)(free_b * 0.7) / 8;            // in uint2
+    if (getenv("GOTOH_B200_ARENA_MB")) budget = ((int64_t)atoll(getenv("GOTOH_B200_ARENA_MB")) << 20) / 8;
+    std::vector<std::pair<int, int>> chunks;               // (first, count)
+    int64_t used_u2 = 0, arena_max = 0;
+    int first = 0;
+    for (size_t k = 0; k < n; ++k) {
+        PairInfo& pi = pairs[k];
+        pi.K = G2K;
+        pi.nblk = pi.M + 1 + 31;                     // T: steps of the wavefront over the (l1+1)-row grid
+        const int64_t nstrips = ((int64_t)pi.N + 1 + 32 * G2K - 1) / (32 * G2K);
+        const int64_t need = nstrips * pi.nblk * 32;
+        if (need > (int64_t)(free_b * 0.9) / 8) return fail(GOTOH_B200_ENOMEM, "pair %lld needs %lld bytes of tie-bit arena", (long long)k, (long long)need * 8);
+        if (used_u2 > 0 && used_u2 + need > budget) { chunks.push_back({first, (int)(k - first)}); first = (int)k; used_u2 = 0; }
+        pi.dir_off = used_u2;
+        used_u2 += need;
+        arena_max = std::max(arena_max, used_u2);
+    }
+    chunks.push_back({first, (int)(n - first)});
+    CU(b.arena.ensure((size_t)arena_max));
+    CU(cudaMemcpy(b.pairs.p, pairs.data(), n * sizeof(PairInfo), cudaMemcpyHostToDevice));
+    run.arena_bytes = arena_max * 8;
+    run.chunks = (int)chunks.size();
+    for (const auto& ch : chunks) {
+        Params p;
+        memset(&p, 0, sizeof(p));
+        p.pairs = b.pairs.p; p.pair_first = ch.first; p.pair_count = ch.second;
+        p.s1_idx = b.idx1.p; p.s2_idx = b.idx2.p; p.dmat = b.dmat.p;
+        p.l = run.l; p.v = run.gop; p.u = run.gep; p.is_global = run.is_global;
+        p.arena = b.arena.p; p.fbnd = b.fbnd.p; p.rbnd = b.rbnd.p; p.bnd_stride = bstride;
+        p.best = b.best.p; p.start_i = b.si.p; p.start_j = b.sj.p;
+        const int g = std::max(1, std::min(grid, (ch.second + 3) / 4));
+        CU(cudaEventRecord(run.ev.e[0], 0));
+        GOTOH_LAUNCH((k2_forward<0>), dim3(g), dim3(128), 0, (cudaStream_t)0, p);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(run.ev.e[1], 0));
+        GOTOH_LAUNCH((k2_reverse<0>), dim3(g), dim3(128), 0, (cudaStream_t)0, p);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(run.ev.e[2], 0));
+        WalkParams2 wp;
+        memset(&wp, 0, sizeof(wp));
+        wp.pairs = b.pairs.p; wp.pair_first = ch.first; wp.pair_count = ch.second;
+        wp.arena = reinterpret_cast<const uint8_t*>(b.arena.p);
+        wp.best = b.best.p; wp.start_i = b.si.p; wp.start_j = b.sj.p;
+        wp.ops = b.ops.p; wp.nops = b.nops.p; wp.i0 = b.i0.p; wp.j0 = b.j0.p; wp.out_len = b.lenp.p; wp.score = b.score.p;
+        GOTOH_LAUNCH(k2_walk, dim3((ch.second + 127) / 128), dim3(128), 0, (cudaStream_t)0, wp);
+        CU(cudaGetLastError());
+        const int rc = g2_emit(b, run, ch.first, ch.second);
+        if (rc) return rc;
+        run.launches += 2;
+    }
+    return 0;
+}
+
+// ---- tuned kernels (gotoh2_fast.cuh): strip tasks, bit-plane tie codes --------------------------------------
+template <int K, bool MULTI, bool BITS>
+int g2_launch_fwd(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
+    using namespace gotoh::g2f;
+    const size_t per_warp = Smem<K>::per_warp(run.l);
+    const size_t smem = per_warp * 4;
+    if (smem > 220 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
+    CU(cudaFuncSetAttribute(k2f<K, MULTI, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
+    const int grid = std::max(1, std::min((ntasks + 3) / 4, run.sm_count * ctas_per_sm));
+    GOTOH_LAUNCH((k2f<K, MULTI, BITS>), dim3(grid), dim3(128), smem, (cudaStream_t)0, p);
+    CU(cudaGetLastError());
+    return 0;
+}
+template <int K, bool MULTI>
+int g2_launch_rev(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
+    using namespace gotoh::g2f;
+    const int grid = std::max(1, std::min((ntasks + 3) / 4, run.sm_count * 4));
+    GOTOH_LAUNCH((k2r<K, MULTI>), dim3(grid), dim3(128), 0, (cudaStream_t)0, p);
+    CU(cudaGetLastError());
+    return 0;
+}
+template <int K>
+int g2_launch_group(G2Run& run, const gotoh::g2f::Params& p, int ntasks, bool multi, int phase) {
+    if (phase == 0) {
+        if (run.score_only) return multi ? g2_launch_fwd<K, true, false>(run, p, ntasks) : g2_launch_fwd<K, false, false>(run, p, ntasks);
+        return multi ? g2_launch_fwd<K, true, true>(run, p, ntasks) : g2_launch_fwd<K, false, true>(run, p, ntasks);
+    }
+    return multi ? g2_launch_rev<K, true>(run, p, ntasks) : g2_launch_rev<K, false>(run, p, ntasks);
+}
+
+int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
+    using namespace gotoh::g2f;
+    const size_t n = (size_t)run.n;
+    static const int kK[] = {2, 3, 4, 6, 8};
+    // ---- geometry per pair: K columns per lane, strips, blocks; chunks by arena budget ----------------------
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    int64_t budget = (int64_t)(free_b * 0.7) / 32;           // in uint4 per plane pair (two planes)
+    if (getenv("GOTOH_B200_ARENA_MB")) budget = ((int64_t)atoll(getenv("GOTOH_B200_ARENA_MB")) << 20) / 32;
+    if (run.score_only) budget = (int64_t)1 << 60;
+    std::vector<Extra> extra(n);
+    struct Chunk { int first, count; int64_t slots, bnd; };
+    std::vector<Chunk> chunks;
+    int64_t used = 0, arena_max = 0, slots = 0, bnd = 0, slots_max = 0, bnd_max = 0;
+    int first = 0;
+    for (size_t k = 0; k < n; ++k) {
+        PairInfo& pi = pairs[k];
+        int K = 8;
+        for (int x : kK) if (32 * x >= pi.N) { K = x; break; }
+        pi.K = (int16_t)K;
+        pi.nblk = (pi.M + 31 + FSTEPS - 1) / FSTEPS;
+        const int64_t nstrips = ((int64_t)pi.N + 32 * K - 1) / (32 * K);
+        const int64_t need = nstrips * pi.nblk * 32;
+        if (!run.score_only && need > (int64_t)(free_b * 0.9) / 32)
+            return fail(GOTOH_B200_ENOMEM, "pair %lld needs %lld bytes of tie-bit arena", (long long)k, (long long)need * 32);
+        if (used > 0 && (used + need > budget || slots + nstrips > 0x3fffffff)) {
+            chunks.push_back({first, (int)(k - first), slots, bnd});
+            first = (int)k; used = 0; slots = 0; bnd = 0;
+        }
+        pi.dir_off = used;
+        used += need;
+        extra[k].slot0 = (int32_t)slots;
+        extra[k].nstrips = (int32_t)nstrips;
+        extra[k].bnd_off = bnd;
+        slots += nstrips;
+        bnd += (nstrips - 1) * (int64_t)(pi.M + 2);
+        arena_max = std::max(arena_max, used);
+        slots_max = std::max(slots_max, slots);
+        bnd_max = std::max(bnd_max, bnd);
+    }
+    chunks.push_back({first, (int)(n - first), slots, bnd});
+    if (!run.score_only) { CU(b.lo.ensure((size_t)arena_max)); CU(b.hi.ensure((size_t)arena_max)); }
+    CU(b.extra.ensure(n));
+    CU(b.tasks.ensure((size_t)slots_max));
+    CU(b.prog.ensure((size_t)slots_max * 2 + 2));
+    CU(b.part.ensure((size_t)slots_max * 2));
+    CU(b.fbnd.ensure((size_t)bnd_max + 1));
+    CU(b.rbnd.ensure((size_t)bnd_max + 1));
+    CU(b.counters.ensure(16));
+    CU(cudaMemcpy(b.pairs.p, pairs.data(), n * sizeof(PairInfo), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(b.extra.p, extra.data(), n * sizeof(Extra), cudaMemcpyHostToDevice));
+    run.arena_bytes = run.score_only ? 0 : arena_max * 32;
+    run.chunks = (int)chunks.size();
+
+    std::vector<StripTask> tasks;
+    for (const auto& ch : chunks) {
+        // groups: (K, single strip) and (8, multi strip); tasks of one group are contiguous in b.tasks
+        struct Group { int K; bool multi; int first, count; };
+        std::vector<Group> groups;
+        tasks.clear();
+        for (int gi = 0; gi < 6; ++gi) {
+            const int K = gi < 5 ? kK[gi] : 8;
+            const bool multi = (gi == 5);
+            const int t0 = (int)tasks.size();
+            for (int k = ch.first; k < ch.first + ch.count; ++k) {
+                if (pairs[(size_t)k].K != K || (extra[(size_t)k].nstrips > 1) != multi) continue;
+                for (int s = 0; s < extra[(size_t)k].nstrips; ++s) tasks.push_back({k, s});
+            }
+            if ((int)tasks.size() > t0) groups.push_back({K, multi, t0, (int)tasks.size() - t0});
+        }
+        CU(cudaMemcpy(b.tasks.p, tasks.data(), tasks.size() * sizeof(StripTask), cudaMemcpyHostToDevice));
+        CU(cudaMemset(b.prog.p, 0, (size_t)ch.slots * sizeof(int32_t)));                       // forward: rows published
+        CU(cudaMemset(b.prog.p + slots_max, 0x7f, ((size_t)ch.slots + 2) * sizeof(int32_t)));  // reverse: lowest row done
+        CU(cudaMemset(b.counters.p, 0, 16 * sizeof(uint32_t)));
+        Params p;
+        memset(&p, 0, sizeof(p));
+        p.pairs = b.pairs.p; p.extra = b.extra.p;
+        p.s1_idx = b.idx1.p; p.s2_idx = b.idx2.p; p.dmat = b.dmat.p;
+        p.l = run.l; p.v = run.gop; p.u = run.gep; p.is_global = run.is_global;
+        p.two = 2; p.four = 4;
+        p.lo = b.lo.p; p.hi = b.hi.p; p.bnd = b.fbnd.p; p.rbnd = b.rbnd.p;
+        p.prog_f = b.prog.p; p.prog_r = b.prog.p + slots_max;
+        p.part_min = b.part.p; p.part_j = b.part.p + slots_max;
+        p.best = b.best.p; p.start_i = b.si.p; p.start_j = b.sj.p;
+        CU(cudaEventRecord(run.ev.e[0], 0));
+        for (size_t g = 0; g < groups.size(); ++g) {
+            p.tasks = b.tasks.p + groups[g].first; p.task_count = groups[g].count;
+            p.counter_f = b.counters.p + g;
+            int rc = 0;
+            switch (groups[g].K) {
+                case 2: rc = g2_launch_group<2>(run, p, groups[g].count, groups[g].multi, 0); break;
+                case 3: rc = g2_launch_group<3>(run, p, groups[g].count, groups[g].multi, 0); break;
+                case 4: rc = g2_launch_group<4>(run, p, groups[g].count, groups[g].multi, 0); break;
+                case 6: rc = g2_launch_group<6>(run, p, groups[g].count, groups[g].multi, 0); break;
+                default: rc = g2_launch_group<8>(run, p, groups[g].count, groups[g].multi, 0); break;
+            }
+            if (rc) return rc;
+            ++run.launches;
+        }
+        CU(cudaEventRecord(run.ev.e[1], 0));
+        if (!run.score_only) {
+            for (size_t g = 0; g < groups.size(); ++g) {
+                p.tasks = b.tasks.p + groups[g].first; p.task_count = groups[g].count;
+                p.counter_r = b.counters.p + 8 + g;
+                int rc = 0;
+                switch (groups[g].K) {
+                    case 2: rc = g2_launch_group<2>(run, p, groups[g].count, groups[g].multi, 1); break;
+                    case 3: rc = g2_launch_group<3>(run, p, groups[g].count, groups[g].multi, 1); break;
+                    case 4: rc = g2_launch_group<4>(run, p, groups[g].count, groups[g].multi, 1); break;
+                    case 6: rc = g2_launch_group<6>(run, p, groups[g].count, groups[g].multi, 1); break;
+                    default: rc = g2_launch_group<8>(run, p, groups[g].count, groups[g].multi, 1); break;
+                }
+                if (rc) return rc;
+                ++run.launches;
+            }
+        }
+        CU(cudaEventRecord(run.ev.e[2], 0));
+        if (run.score_only) {
+            CU(cudaEventSynchronize(run.ev.e[2]));
+            float a = 0;
+            CU(cudaEventElapsedTime(&a, run.ev.e[0], run.ev.e[1]));
+            run.ms_f += a;
+            continue;
+        }
+        gotoh::g2f::WalkParams wp;
+        memset(&wp, 0, sizeof(wp));
+        wp.pairs = b.pairs.p; wp.pair_first = ch.first; wp.pair_count = ch.count;
+        wp.hi = reinterpret_cast<const uint32_t*>(b.hi.p);
+        wp.best = b.best.p; wp.start_i = b.si.p; wp.start_j = b.sj.p;
+        wp.ops = b.ops.p; wp.nops = b.nops.p; wp.i0 = b.i0.p; wp.j0 = b.j0.p; wp.out_len = b.lenp.p; wp.score = b.score.p;
+        GOTOH_LAUNCH(k2f_walk, dim3((ch.count + 127) / 128), dim3(128), 0, (cudaStream_t)0, wp);
+        CU(cudaGetLastError());
+        const int rc = g2_emit(b, run, ch.first, ch.count);
+        if (rc) return rc;
+    }
+    return 0;
+}
 
 // gotoh2.py:70-72 on bytes: ASCII upper-case, then every byte that is not in the alphabet becomes '?'.
 inline uint8_t g2_clean(uint8_t c, const bool* in_alpha) {
@@ -15,7 +313,7 @@ inline uint8_t g2_clean(uint8_t c, const bool* in_alpha) {
 int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, int64_t n_s1, const int32_t* s1_idx,
                    const uint8_t* s2_bytes, const int64_t* s2_off, int64_t n_pairs, int gop, int gep, int is_global,
                    const char* alphabet, const int32_t* matrix, uint8_t* out1, uint8_t* out2, const int64_t* out_off,
-                   int32_t* out_len, int32_t* out_score) {
+                   int32_t* out_len, int32_t* out_score, bool score_only) {
     using namespace gotoh::g2;
     const int l = (int)strlen(alphabet);
     if (l < 1 || l > 32) return fail(GOTOH_B200_EINVAL, "alphabet length %d not in 1..32", l);
@@ -53,11 +351,15 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
         }
         return 0;
     };
+    // every first sequence carries REF_PAD zero bytes on both sides: the wavefront reads the row class a few
+    // rows before row 1 and after row l1 without a bounds check
+    h_raw1.assign(gotoh::REF_PAD, 0); h_idx1.assign(gotoh::REF_PAD, 0);
     for (size_t x = 0; x < used.size(); ++x) {
         const int64_t r = used[x];
         pos1[x] = (int64_t)h_raw1.size();
         const int rc = add_seq(s1_bytes + s1_off[r], s1_off[r + 1] - s1_off[r], h_raw1, h_idx1, "seq1", (long long)r);
         if (rc) return rc;
+        h_raw1.insert(h_raw1.end(), gotoh::REF_PAD, 0); h_idx1.insert(h_idx1.end(), gotoh::REF_PAD, 0);
     }
     std::vector<PairInfo> pairs((size_t)n_pairs);
     int64_t ops_words = 0, max_rows = 0;
@@ -76,10 +378,12 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
         pi.nblk = pi.M + 1 + 31;                     // T: steps of the wavefront over the (l1+1)-row grid
         pi.K = G2K;
         pi.orig = (int32_t)k;
-        pi.out_off = out_off[k] - out_off[0];
-        const int64_t cap = out_off[k + 1] - out_off[k];
-        if (cap < (int64_t)pi.M + pi.N || cap > 0x7fffffffLL) return fail(GOTOH_B200_ERANGE, "pair %lld: output stride < l1+l2", (long long)k);
-        pi.out_cap = (int32_t)cap;
+        if (!score_only) {
+            pi.out_off = out_off[k] - out_off[0];
+            const int64_t cap = out_off[k + 1] - out_off[k];
+            if (cap < (int64_t)pi.M + pi.N || cap > 0x7fffffffLL) return fail(GOTOH_B200_ERANGE, "pair %lld: output stride < l1+l2", (long long)k);
+            pi.out_cap = (int32_t)cap;
+        }
         if (ops_words + (pi.M + pi.N + 15) / 16 > 0x7fffffffLL) return fail(GOTOH_B200_ERANGE, "op-script arena too large; split the batch");
         pi.ops_off = (int32_t)ops_words;
         ops_words += (pi.M + pi.N + 15) / 16;
@@ -96,92 +400,40 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    struct Bufs {
-        DevBuf<uint8_t> raw1, idx1, raw2, idx2, o1, o2, rbnd;
-        DevBuf<PairInfo> pairs;
-        DevBuf<int32_t> dmat, best, si, sj, nops, i0, j0, lenp, score, olen, oscore;
-        DevBuf<uint32_t> ops;
-        DevBuf<uint2> arena;
-        DevBuf<int2> fbnd;
-        ~Bufs() {
-            raw1.release(); idx1.release(); raw2.release(); idx2.release(); o1.release(); o2.release(); rbnd.release();
-            pairs.release(); dmat.release(); best.release(); si.release(); sj.release(); nops.release(); i0.release();
-            j0.release(); lenp.release(); score.release(); olen.release(); oscore.release(); ops.release(); arena.release();
-            fbnd.release();
-        }
-    } b;
+    G2Bufs b;
     const size_t n = (size_t)n_pairs;
-    const int64_t out_bytes = out_off[n_pairs] - out_off[0];
+    const int64_t out_bytes = score_only ? 0 : out_off[n_pairs] - out_off[0];
     CU(b.raw1.ensure(h_raw1.size())); CU(b.idx1.ensure(h_idx1.size()));
     CU(b.raw2.ensure(h_raw2.size())); CU(b.idx2.ensure(h_idx2.size()));
     CU(b.pairs.ensure(n)); CU(b.dmat.ensure((size_t)l * l));
     CU(b.best.ensure(n)); CU(b.si.ensure(n)); CU(b.sj.ensure(n)); CU(b.nops.ensure(n)); CU(b.i0.ensure(n)); CU(b.j0.ensure(n));
     CU(b.lenp.ensure(n)); CU(b.score.ensure(n)); CU(b.olen.ensure(n)); CU(b.oscore.ensure(n));
     CU(b.ops.ensure((size_t)ops_words));
-    CU(b.o1.ensure((size_t)out_bytes)); CU(b.o2.ensure((size_t)out_bytes));
-    const int grid = prop.multiProcessorCount * 4, nwarps = grid * 4;
-    const int64_t bstride = (max_rows + 2 + 15) & ~15LL;
-    CU(b.fbnd.ensure((size_t)(nwarps * bstride)));
-    CU(b.rbnd.ensure((size_t)(nwarps * bstride)));
-
-    // arena chunks: one byte per grid cell, [strip][step][lane] x 8 bytes
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    int64_t budget = (int64_t)(free_b * 0.7) / 8;            // in uint2
-    if (getenv("GOTOH_B200_ARENA_MB")) budget = ((int64_t)atoll(getenv("GOTOH_B200_ARENA_MB")) << 20) / 8;
-    std::vector<std::pair<int, int>> chunks;               // (first, count)
-    int64_t used_u2 = 0, arena_max = 0;
-    int first = 0;
-    for (int64_t k = 0; k < n_pairs; ++k) {
-        PairInfo& pi = pairs[(size_t)k];
-        const int64_t nstrips = ((int64_t)pi.N + 1 + 32 * G2K - 1) / (32 * G2K);
-        const int64_t need = nstrips * pi.nblk * 32;
-        if (need > (int64_t)(free_b * 0.9) / 8) return fail(GOTOH_B200_ENOMEM, "pair %lld needs %lld bytes of tie-bit arena", (long long)k, (long long)need * 8);
-        if (used_u2 > 0 && used_u2 + need > budget) { chunks.push_back({first, (int)(k - first)}); first = (int)k; used_u2 = 0; }
-        pi.dir_off = used_u2;
-        used_u2 += need;
-        arena_max = std::max(arena_max, used_u2);
-    }
-    chunks.push_back({first, (int)(n_pairs - first)});
-    CU(b.arena.ensure((size_t)arena_max));
-
+    if (!score_only) { CU(b.o1.ensure((size_t)out_bytes)); CU(b.o2.ensure((size_t)out_bytes)); }
     CU(cudaMemcpy(b.raw1.p, h_raw1.data(), h_raw1.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(b.idx1.p, h_idx1.data(), h_idx1.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(b.raw2.p, h_raw2.data(), h_raw2.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(b.idx2.p, h_idx2.data(), h_idx2.size(), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(b.pairs.p, pairs.data(), n * sizeof(PairInfo), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(b.dmat.p, matrix, (size_t)l * l * sizeof(int32_t), cudaMemcpyHostToDevice));
 
-    for (const auto& ch : chunks) {
-        Params p;
-        memset(&p, 0, sizeof(p));
-        p.pairs = b.pairs.p; p.pair_first = ch.first; p.pair_count = ch.second;
-        p.s1_idx = b.idx1.p; p.s2_idx = b.idx2.p; p.dmat = b.dmat.p;
-        p.l = l; p.v = gop; p.u = gep; p.is_global = is_global ? 1 : 0;
-        p.arena = b.arena.p; p.fbnd = b.fbnd.p; p.rbnd = b.rbnd.p; p.bnd_stride = bstride;
-        p.best = b.best.p; p.start_i = b.si.p; p.start_j = b.sj.p;
-        const int g = std::max(1, std::min(grid, (ch.second + 3) / 4));
-        GOTOH_LAUNCH((k2_forward<0>), dim3(g), dim3(128), 0, (cudaStream_t)0, p);
-        CU(cudaGetLastError());
-        GOTOH_LAUNCH((k2_reverse<0>), dim3(g), dim3(128), 0, (cudaStream_t)0, p);
-        CU(cudaGetLastError());
-        WalkParams2 wp;
-        memset(&wp, 0, sizeof(wp));
-        wp.pairs = b.pairs.p; wp.pair_first = ch.first; wp.pair_count = ch.second;
-        wp.arena = reinterpret_cast<const uint8_t*>(b.arena.p);
-        wp.best = b.best.p; wp.start_i = b.si.p; wp.start_j = b.sj.p;
-        wp.ops = b.ops.p; wp.nops = b.nops.p; wp.i0 = b.i0.p; wp.j0 = b.j0.p; wp.out_len = b.lenp.p; wp.score = b.score.p;
-        GOTOH_LAUNCH(k2_walk, dim3((ch.second + 127) / 128), dim3(128), 0, (cudaStream_t)0, wp);
-        CU(cudaGetLastError());
-        EmitParams ep;
-        memset(&ep, 0, sizeof(ep));
-        ep.pairs = b.pairs.p; ep.pair_first = ch.first; ep.pair_count = ch.second;
-        ep.ref_raw = b.raw1.p; ep.qry = b.raw2.p; ep.ops = b.ops.p; ep.nops = b.nops.p;
-        ep.i0 = b.i0.p; ep.j0 = b.j0.p; ep.end_i = b.si.p; ep.end_j = b.sj.p;
-        ep.out_len_plan = b.lenp.p; ep.score_plan = b.score.p;
-        ep.out_ref = b.o1.p; ep.out_qry = b.o2.p; ep.out_len = b.olen.p; ep.out_score = b.oscore.p;
-        GOTOH_LAUNCH(k_emit, dim3((ch.second + 3) / 4), dim3(128), 0, (cudaStream_t)0, ep);
-        CU(cudaGetLastError());
+    G2Run run;
+    run.n = n_pairs; run.l = l; run.gop = gop; run.gep = gep; run.is_global = is_global ? 1 : 0;
+    run.score_only = score_only; run.sm_count = prop.multiProcessorCount; run.max_rows = max_rows;
+    if (!run.ev.create()) return fail(GOTOH_B200_ECUDA, "cudaEventCreate failed");
+    const char* force = getenv("GOTOH_B200_GOTOH2");          // tests: "general" pins the un-tuned kernels (still a GPU path)
+    const bool fast = gop >= 0 && gep >= 0 && !(force && !strcmp(force, "general"));
+    if (score_only && !fast) return fail(GOTOH_B200_ERANGE, "score-only mode needs non-negative penalties");
+    const int rc = fast ? g2_run_fast(b, run, pairs) : g2_run_general(b, run, pairs);
+    if (rc) return rc;
+
+    g2_stats[0] = (double)cells; g2_stats[1] = run.ms_f + run.ms_r + run.ms_w; g2_stats[2] = run.ms_f; g2_stats[3] = run.ms_r;
+    g2_stats[4] = run.ms_w; g2_stats[5] = run.launches; g2_stats[6] = (double)run.arena_bytes; g2_stats[7] = (double)run.chunks;
+    g2_stats[8] = (double)(h_raw1.size() * 2 + h_raw2.size() * 2 + n * sizeof(PairInfo) + (size_t)l * l * 4);
+    g2_stats[9] = (double)((score_only ? 0 : 2 * out_bytes) + 8 * (int64_t)n);
+    if (score_only) {
+        CU(cudaMemcpy(out_score, b.best.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int64_t k = 0; k < n_pairs; ++k) out_score[k] = -out_score[k];
+        return GOTOH_B200_OK;
     }
     CU(cudaMemcpy(out1 + out_off[0], b.o1.p, (size_t)out_bytes, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(out2 + out_off[0], b.o2.p, (size_t)out_bytes, cudaMemcpyDeviceToHost));
@@ -194,6 +446,12 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
 }
 
 }  // namespace
+
+extern "C" int32_t gotoh_b200_gotoh2_last_stats(double* out, int32_t n) {
+    if (!out || n < 0) return fail(GOTOH_B200_EINVAL, "NULL argument");
+    for (int x = 0; x < n && x < 10; ++x) out[x] = g2_stats[x];
+    return n < 10 ? n : 10;
+}
 
 extern "C" int32_t gotoh_b200_gotoh2_align_batch(const uint8_t* s1_bytes, const int64_t* s1_off, int64_t n_s1,
                                                  const int32_t* s1_idx, const uint8_t* s2_bytes, const int64_t* s2_off,
@@ -211,7 +469,7 @@ extern "C" int32_t gotoh_b200_gotoh2_align_batch(const uint8_t* s1_bytes, const 
     if (n_pairs == 0) return GOTOH_B200_OK;
     try {
         return g2_align_batch(device, s1_bytes, s1_off, n_s1, s1_idx, s2_bytes, s2_off, n_pairs, gop, gep, is_global,
-                              alphabet, matrix, out1, out2, out_off, out_len, out_score);
+                              alphabet, matrix, out1, out2, out_off, out_len, out_score, false);
     } catch (const std::bad_alloc&) {
         return fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
     }

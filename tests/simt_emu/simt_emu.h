@@ -190,6 +190,9 @@ static inline void __nanosleep(unsigned) { simt::yield(); }
 // DPX (sm_90+/sm_100a: VIADDMNMX, VIMNMX3 and their .S16x2 forms)
 static inline int __viaddmax_s32(int a, int b, int c) { return max((int)((unsigned)a + (unsigned)b), c); }
 static inline int __vimax3_s32(int a, int b, int c) { return max(max(a, b), c); }
+static inline int __viaddmin_s32(int a, int b, int c) { return min((int)((unsigned)a + (unsigned)b), c); }
+static inline int __viaddmin_s32_relu(int a, int b, int c) { return max(min((int)((unsigned)a + (unsigned)b), c), 0); }
+static inline int __vimin3_s32(int a, int b, int c) { return min(min(a, b), c); }
 static inline int16_t simt_lo(unsigned x) { return (int16_t)(x & 0xffff); }
 static inline int16_t simt_hi(unsigned x) { return (int16_t)(x >> 16); }
 static inline unsigned simt_pack(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
