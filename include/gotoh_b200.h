@@ -150,7 +150,19 @@ int32_t gotoh_b200_gotoh2_align_batch(const uint8_t* s1_bytes, const int64_t* s1
                                       uint8_t* out1, uint8_t* out2, const int64_t* out_off,
                                       int32_t* out_len, int32_t* out_score, int32_t device);
 
-/* Statistics of the calling thread's last gotoh_b200_gotoh2_align_batch (benchmarks, tests): fills up to
+/*
+ * NEXT #3: the edit distance of the seed filter in remap.sam_to_conseqs,
+ * `Levenshtein.distance(relevant_seed, relevant_conseq)` (micall/core/remap.py:250; third-party python-Levenshtein,
+ * INSTALL.md:8,22).  out_dist[k] = unit-cost insert/delete/substitute distance between
+ * a_bytes[a_off[k]..a_off[k+1]) and b_bytes[b_off[k]..b_off[k+1]), compared byte by byte (no cleaning); empty
+ * strings are allowed.  Runs the score-only forward kernel (no traceback arena).  At most 30 distinct bytes may
+ * occur on BOTH sides of the batch (GOTOH_B200_ERANGE otherwise).
+ */
+int32_t gotoh_b200_edit_distance_batch(const uint8_t* a_bytes, const int64_t* a_off,
+                                       const uint8_t* b_bytes, const int64_t* b_off, int64_t n_pairs,
+                                       int32_t* out_dist, int32_t device);
+
+/* Statistics of the calling thread's last gotoh_b200_gotoh2_align_batch or gotoh_b200_edit_distance_batch (benchmarks, tests): fills up to
  * n <= 10 doubles and returns how many: 0 grid cells sum (l1+1)(l2+1), 1 device ms of all kernels (CUDA
  * events), 2 forward ms, 3 reverse-sweep ms, 4 walk+emit ms, 5 kernel launches, 6 tie-bit arena bytes,
  * 7 arena chunks, 8 bytes copied H2D, 9 bytes copied D2H. */

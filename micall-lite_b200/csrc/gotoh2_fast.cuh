@@ -52,6 +52,7 @@ struct Params {
     const int32_t* dmat;        // l*l substitution scores (gotoh2.py:47-64)
     int32_t l, v, u, is_global; // v = gap open, u = gap extend (_gotoh2.c:31-32)
     uint32_t two, four;         // == 2, 4 at run time; opaque so acc*two+x stays an IMAD (FMA pipe)
+    uint32_t neg1;              // == 0xffffffff at run time: c - r as r*neg1 + c on the FMA pipe
     uint4* lo;                  // plane 0: code_DE | code_FG << 16, one word per lane-step
     uint4* hi;                  // plane 1: a | b << 8 | c << 16 (k2f: forward bits, k2r: final bits)
     int2* bnd;                  // forward strip boundaries (R~, q~) per row
@@ -90,7 +91,7 @@ struct Fwd {
     enum { K4 = (K + 3) / 4, KMASK = (1 << K) - 1 };
     int lane, M, N, j0, strip, u, v, c1v, c2v;
     bool last_strip;
-    unsigned two, four, keep;
+    unsigned two, four, keep, neg1;
     int injq, c0run, c0step;
     unsigned CA3;                  // (KMASK + off_K) * 0x010101
     const uint4* prof_lane;
@@ -169,7 +170,7 @@ struct Fwd {
                     const int p = __viaddmin_s32(R[k], v, P[k]);                  // _gotoh2.c:156
                     const int dg = rdiag + ev[kk];                                // _gotoh2.c:185
                     const int r = __vimin3_s32(dg, p, q);                         // _gotoh2.c:186-187
-                    const int nr = c1v - r;
+                    const int nr = (int)((unsigned)r * neg1 + (unsigned)c1v);    // (1 - v) - r, on the FMA pipe
                     if (BITS) {
                         accA = accA * two + (unsigned)__viaddmin_s32(p, nr, c2v);   // (1-v) + [R != p]   (_gotoh2.c:190-192)
                         accB = accB * two + (unsigned)__viaddmin_s32(q, nr, c2v);   // (1-v) + [R != q]   (:193-195)
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(128, 4) k2f(const Params p) {
     w.lane = lane;
     w.u = p.u; w.v = p.v;
     w.c1v = 1 - p.v; w.c2v = 2 - p.v;
-    w.two = p.two; w.four = p.four;
+    w.two = p.two; w.four = p.four; w.neg1 = p.neg1;
     w.prof_lane = prof + lane;
     w.ring = reinterpret_cast<int2*>(my_smem + (size_t)p.l * K4 * 32 * 16);
     w.CA3 = (unsigned)(W::KMASK + (1 - p.v) * W::KMASK) * 0x010101u;
@@ -514,10 +515,16 @@ __global__ void __launch_bounds__(128) k2f_walk(const WalkParams p) {
     uint32_t cur = 0;
     int n = 0;
     bool failed = false;
+    const uint4* hi4 = reinterpret_cast<const uint4*>(p.hi);
+    int64_t cached_at = -1;
+    uint4 cached = make_uint4(0, 0, 0, 0);
     while (i > 0 && j > 0) {
         const int jj = j - 1, strip = jj / (32 * K), rem = jj - strip * 32 * K, lane = rem / K, k = rem - lane * K;
         const int tt = i + lane - 1, tb = tt >> 2, s = tt & 3;
-        const uint32_t w = p.hi[((pr.dir_off + ((int64_t)strip * nblk + tb) * 32 + lane) << 2) + s];
+        // one uint4 holds 4 consecutive rows of this lane's K columns: a diagonal run stays inside it for ~4 cells
+        const int64_t at = pr.dir_off + ((int64_t)strip * nblk + tb) * 32 + lane;
+        if (at != cached_at) { cached = hi4[at]; cached_at = at; }
+        const uint32_t w = s == 0 ? cached.x : s == 1 ? cached.y : s == 2 ? cached.z : cached.w;
         const int bit = K - 1 - k;
         uint32_t d;
         if ((w >> bit) & 1u) { d = DIR_UP; --i; }                         // vertical first (_gotoh2.c:381-388)

@@ -245,7 +245,7 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
         p.pairs = b.pairs.p; p.extra = b.extra.p;
         p.s1_idx = b.idx1.p; p.s2_idx = b.idx2.p; p.dmat = b.dmat.p;
         p.l = run.l; p.v = run.gop; p.u = run.gep; p.is_global = run.is_global;
-        p.two = 2; p.four = 4;
+        p.two = 2; p.four = 4; p.neg1 = 0xffffffffu;
         p.lo = b.lo.p; p.hi = b.hi.p; p.bnd = b.fbnd.p; p.rbnd = b.rbnd.p;
         p.prog_f = b.prog.p; p.prog_r = b.prog.p + slots_max;
         p.part_min = b.part.p; p.part_j = b.part.p + slots_max;
@@ -304,23 +304,18 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
     return 0;
 }
 
-// gotoh2.py:70-72 on bytes: ASCII upper-case, then every byte that is not in the alphabet becomes '?'.
-inline uint8_t g2_clean(uint8_t c, const bool* in_alpha) {
-    if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
-    return in_alpha[c] ? c : (uint8_t)'?';
-}
+// Byte -> (cleaned byte, class index) tables of one side of the grid.  gotoh2.py:70-72: ASCII upper-case, then every
+// byte that is not in the alphabet becomes '?'; cls < 0 marks a byte the alphabet cannot express at all.
+struct G2Map {
+    uint8_t clean[256];
+    int16_t cls[256];
+};
 
 int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, int64_t n_s1, const int32_t* s1_idx,
                    const uint8_t* s2_bytes, const int64_t* s2_off, int64_t n_pairs, int gop, int gep, int is_global,
-                   const char* alphabet, const int32_t* matrix, uint8_t* out1, uint8_t* out2, const int64_t* out_off,
-                   int32_t* out_len, int32_t* out_score, bool score_only) {
+                   int l, const G2Map& map1, const G2Map& map2, const int32_t* matrix, uint8_t* out1, uint8_t* out2,
+                   const int64_t* out_off, int32_t* out_len, int32_t* out_score, bool score_only) {
     using namespace gotoh::g2;
-    const int l = (int)strlen(alphabet);
-    if (l < 1 || l > 32) return fail(GOTOH_B200_EINVAL, "alphabet length %d not in 1..32", l);
-    bool in_alpha[256] = {false};
-    int map[256];
-    for (int c = 0; c < 256; ++c) map[c] = -1;
-    for (int x = 0; x < l; ++x) { in_alpha[(uint8_t)alphabet[x]] = true; map[(uint8_t)alphabet[x]] = x; }   // _gotoh2.c:68-77
 
     // ---- clean + index every used first sequence once, every second sequence ---------------------
     std::vector<int32_t> local;
@@ -338,16 +333,18 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
     }
     std::vector<int64_t> pos1(used.size());
     std::vector<uint8_t> h_raw1, h_idx1, h_raw2, h_idx2;
-    auto add_seq = [&](const uint8_t* s, int64_t len, std::vector<uint8_t>& raw, std::vector<uint8_t>& idx, const char* what,
-                       long long id) -> int {
+    auto add_seq = [&](const uint8_t* s, int64_t len, const G2Map& mp, std::vector<uint8_t>& raw, std::vector<uint8_t>& idx,
+                       const char* what, long long id) -> int {
         if (len <= 0) return fail(GOTOH_B200_EEMPTY, "%s %lld is empty (gotoh2.py:84-85 asserts non-empty)", what, id);
         if (len >= (1 << 24)) return fail(GOTOH_B200_ERANGE, "%s %lld too long", what, id);
+        const size_t at = raw.size();
+        raw.resize(at + (size_t)len);
+        idx.resize(at + (size_t)len);
         for (int64_t x = 0; x < len; ++x) {
-            if (s[x] == 0) return fail(GOTOH_B200_EDOMAIN, "%s %lld contains a NUL byte", what, id);
-            const uint8_t c = g2_clean(s[x], in_alpha);
-            if (map[c] < 0) return fail(GOTOH_B200_EDOMAIN, "%s %lld: byte 0x%02x is not in the alphabet and the alphabet has no '?'", what, id, s[x]);
-            raw.push_back(c);
-            idx.push_back((uint8_t)map[c]);
+            const int c = mp.cls[s[x]];
+            if (c < 0) return fail(GOTOH_B200_EDOMAIN, "%s %lld: byte 0x%02x is not in the alphabet and the alphabet has no '?'", what, id, s[x]);
+            raw[at + (size_t)x] = mp.clean[s[x]];
+            idx[at + (size_t)x] = (uint8_t)c;
         }
         return 0;
     };
@@ -357,7 +354,7 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
     for (size_t x = 0; x < used.size(); ++x) {
         const int64_t r = used[x];
         pos1[x] = (int64_t)h_raw1.size();
-        const int rc = add_seq(s1_bytes + s1_off[r], s1_off[r + 1] - s1_off[r], h_raw1, h_idx1, "seq1", (long long)r);
+        const int rc = add_seq(s1_bytes + s1_off[r], s1_off[r + 1] - s1_off[r], map1, h_raw1, h_idx1, "seq1", (long long)r);
         if (rc) return rc;
         h_raw1.insert(h_raw1.end(), gotoh::REF_PAD, 0); h_idx1.insert(h_idx1.end(), gotoh::REF_PAD, 0);
     }
@@ -371,7 +368,7 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
         const int64_t u1 = used[(size_t)r];
         pi.ref_pos = pos1[(size_t)r];
         pi.qry_pos = (int64_t)h_raw2.size();
-        const int rc = add_seq(s2_bytes + s2_off[k], s2_off[k + 1] - s2_off[k], h_raw2, h_idx2, "seq2", (long long)k);
+        const int rc = add_seq(s2_bytes + s2_off[k], s2_off[k + 1] - s2_off[k], map2, h_raw2, h_idx2, "seq2", (long long)k);
         if (rc) return rc;
         pi.M = (int32_t)(s1_off[u1 + 1] - s1_off[u1]);
         pi.N = (int32_t)(s2_off[k + 1] - s2_off[k]);
@@ -467,9 +464,81 @@ extern "C" int32_t gotoh_b200_gotoh2_align_batch(const uint8_t* s1_bytes, const 
     if (ndev <= 0) return fail(GOTOH_B200_ENODEVICE, "no CUDA device is visible; libgotoh_b200 has no CPU path");
     if (device < 0 || device >= ndev) return fail(GOTOH_B200_ENODEVICE, "device %d not present (%d visible)", device, ndev);
     if (n_pairs == 0) return GOTOH_B200_OK;
+    const int l = (int)strlen(alphabet);
+    if (l < 1 || l > 32) return fail(GOTOH_B200_EINVAL, "alphabet length %d not in 1..32", l);
+    G2Map mp;
+    int cls_of[256];
+    for (int c = 0; c < 256; ++c) cls_of[c] = -1;
+    for (int x = 0; x < l; ++x) cls_of[(uint8_t)alphabet[x]] = x;                       // _gotoh2.c:68-77
+    for (int c = 0; c < 256; ++c) {
+        int up = (c >= 'a' && c <= 'z') ? c - 32 : c;                                    // gotoh2.py:72 seq.upper()
+        if (cls_of[up] < 0) up = '?';                                                    // gotoh2.py:72 [^alphabet] -> '?'
+        mp.clean[c] = (uint8_t)up;
+        mp.cls[c] = (int16_t)(c == 0 ? -1 : cls_of[up]);                                 // NUL cannot occur in a Python str argument
+    }
     try {
         return g2_align_batch(device, s1_bytes, s1_off, n_s1, s1_idx, s2_bytes, s2_off, n_pairs, gop, gep, is_global,
-                              alphabet, matrix, out1, out2, out_off, out_len, out_score, false);
+                              l, mp, mp, matrix, out1, out2, out_off, out_len, out_score, false);
+    } catch (const std::bad_alloc&) {
+        return fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
+    }
+}
+
+// Levenshtein.distance(a, b) of remap.py:250 (third-party python-Levenshtein, unpinned in INSTALL.md:8,22): unit-cost
+// edit distance = the min-cost global alignment with open 0, extend 1, substitution cost [x != y], i.e. the score-only
+// forward kernel with v = 0, u = 1 and a 0/-1 matrix over the bytes that occur on both sides.
+extern "C" int32_t gotoh_b200_edit_distance_batch(const uint8_t* a_bytes, const int64_t* a_off, const uint8_t* b_bytes,
+                                                  const int64_t* b_off, int64_t n_pairs, int32_t* out_dist, int32_t device) {
+    if (!a_bytes || !a_off || !b_bytes || !b_off || !out_dist) return fail(GOTOH_B200_EINVAL, "NULL pointer argument");
+    if (n_pairs < 0 || n_pairs > 0x7fffffffLL) return fail(GOTOH_B200_EINVAL, "bad count");
+    const int ndev = gotoh_b200_device_count();
+    if (ndev <= 0) return fail(GOTOH_B200_ENODEVICE, "no CUDA device is visible; libgotoh_b200 has no CPU path");
+    if (device < 0 || device >= ndev) return fail(GOTOH_B200_ENODEVICE, "device %d not present (%d visible)", device, ndev);
+    if (n_pairs == 0) return GOTOH_B200_OK;
+    try {
+        // pairs with an empty side need no DP: the distance is the other length
+        std::vector<int64_t> keep;
+        bool in_a[256] = {false}, in_b[256] = {false};
+        for (int64_t k = 0; k < n_pairs; ++k) {
+            const int64_t la = a_off[k + 1] - a_off[k], lb = b_off[k + 1] - b_off[k];
+            if (la < 0 || lb < 0) return fail(GOTOH_B200_EINVAL, "pair %lld: negative length", (long long)k);
+            if (la == 0 || lb == 0) { out_dist[k] = (int32_t)(la + lb); continue; }
+            keep.push_back(k);
+            for (int64_t x = a_off[k]; x < a_off[k + 1]; ++x) in_a[a_bytes[x]] = true;
+            for (int64_t x = b_off[k]; x < b_off[k + 1]; ++x) in_b[b_bytes[x]] = true;
+        }
+        if (keep.empty()) return GOTOH_B200_OK;
+        // classes: one per byte present on both sides, plus "only in a" (l-2) and "only in b" (l-1), which match nothing
+        G2Map ma, mb;
+        int ncommon = 0;
+        for (int c = 0; c < 256; ++c) if (in_a[c] && in_b[c]) ++ncommon;
+        if (ncommon > 30) return fail(GOTOH_B200_ERANGE, "%d distinct bytes occur on both sides; at most 30 are supported", ncommon);
+        const int l = ncommon + 2;
+        int next = 0;
+        for (int c = 0; c < 256; ++c) {
+            ma.clean[c] = mb.clean[c] = (uint8_t)c;
+            if (in_a[c] && in_b[c]) { ma.cls[c] = mb.cls[c] = (int16_t)next++; }
+            else { ma.cls[c] = (int16_t)(l - 2); mb.cls[c] = (int16_t)(l - 1); }
+        }
+        std::vector<int32_t> matrix((size_t)l * l, -1);
+        for (int x = 0; x < ncommon; ++x) matrix[(size_t)x * l + x] = 0;
+        // compact the kept pairs' offsets (bytes stay where they are: offsets need not be contiguous)
+        const size_t m = keep.size();
+        std::vector<int64_t> ao(m + 1), bo(m + 1);
+        std::vector<uint8_t> ab, bb;
+        for (size_t x = 0; x < m; ++x) {
+            const int64_t k = keep[x];
+            ao[x] = (int64_t)ab.size(); bo[x] = (int64_t)bb.size();
+            ab.insert(ab.end(), a_bytes + a_off[k], a_bytes + a_off[k + 1]);
+            bb.insert(bb.end(), b_bytes + b_off[k], b_bytes + b_off[k + 1]);
+        }
+        ao[m] = (int64_t)ab.size(); bo[m] = (int64_t)bb.size();
+        std::vector<int32_t> sc(m);
+        const int rc = g2_align_batch(device, ab.data(), ao.data(), (int64_t)m, nullptr, bb.data(), bo.data(), (int64_t)m, 0, 1, 1,
+                                      l, ma, mb, matrix.data(), nullptr, nullptr, nullptr, nullptr, sc.data(), true);
+        if (rc) return rc;
+        for (size_t x = 0; x < m; ++x) out_dist[keep[x]] = -sc[x];
+        return GOTOH_B200_OK;
     } catch (const std::bad_alloc&) {
         return fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
     }

@@ -20,7 +20,7 @@ SYMBOLS = (
     "gotoh_b200_pairscore_table", "gotoh_b200_align_batch", "gotoh_b200_plan_create",
     "gotoh_b200_plan_run", "gotoh_b200_plan_fetch", "gotoh_b200_plan_destroy",
     "gotoh_b200_plan_stat", "gotoh_b200_host_alloc", "gotoh_b200_host_free", "gotoh_b200_int_peak",
-    "gotoh_b200_release_cache", "gotoh_b200_gotoh2_align_batch", "gotoh_b200_gotoh2_last_stats",
+    "gotoh_b200_release_cache", "gotoh_b200_gotoh2_align_batch", "gotoh_b200_gotoh2_last_stats", "gotoh_b200_edit_distance_batch",
 )
 
 
@@ -71,6 +71,8 @@ class Library:
         lib.gotoh_b200_gotoh2_align_batch.restype = _i32
         lib.gotoh_b200_gotoh2_align_batch.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
                                                       ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp, _vp, _i32]
+        lib.gotoh_b200_edit_distance_batch.restype = _i32
+        lib.gotoh_b200_edit_distance_batch.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i32]
         lib.gotoh_b200_gotoh2_last_stats.restype = _i32
         lib.gotoh_b200_gotoh2_last_stats.argtypes = [_vp, _i32]
         lib.gotoh_b200_release_cache.restype = None

@@ -82,3 +82,17 @@ class Oracle2:
         if rc:
             raise ValueError("gotoh2 oracle rejected input (code %d)" % rc)
         return (o1.raw[:ln.value].decode("ascii"), o2.raw[:ln.value].decode("ascii"), sc.value)
+
+
+def levenshtein(a, b):
+    """Oracle for Levenshtein.distance(a, b) (remap.py:250): oracle/levenshtein_oracle.c."""
+    if not os.path.exists(_o.PORT_SO):
+        _o.build()
+    lib = ctypes.CDLL(_o.PORT_SO)
+    if not hasattr(lib, "levenshtein_oracle"):
+        _o.build()
+        lib = ctypes.CDLL(_o.PORT_SO)
+    lib.levenshtein_oracle.restype = ctypes.c_long
+    lib.levenshtein_oracle.argtypes = [ctypes.c_char_p, ctypes.c_long, ctypes.c_char_p, ctypes.c_long]
+    ab, bb = (a.encode("latin-1") if isinstance(a, str) else bytes(a)), (b.encode("latin-1") if isinstance(b, str) else bytes(b))
+    return int(lib.levenshtein_oracle(ab, len(ab), bb, len(bb)))

@@ -94,6 +94,14 @@ def test_emu_gotoh2_multi_strip_and_interface(emu_aligner, oracle2_port):
         al.align(b"ACGT", "ACGT")                             # gotoh2.py:82
 
 
+def test_emu_gotoh2_general_kernels_still_match(emu_aligner, monkeypatch):
+    """GOTOH_B200_GOTOH2=general pins the un-tuned kernels (the path negative penalties take); same answers."""
+    from gotoh_b200.gotoh2 import Aligner
+    monkeypatch.setenv("GOTOH_B200_GOTOH2", "general")
+    n, bad = _check_golden(lambda *a: Aligner(*a, library=emu_aligner._libobj), max_cells=2e3)
+    assert n >= 300 and not bad, bad[:5]
+
+
 @pytest.mark.gpu
 def test_gpu_gotoh2_golden_incl_reference_unit_tests(gpu_aligner):
     from gotoh_b200.gotoh2 import Aligner

@@ -64,18 +64,18 @@ def classify(op):
     return "other"
 
 
-def hot_block(ins, steps):
-    """Shortest region ending at an STG.E.128 and holding exactly 2*steps SHFL.UP."""
+def hot_block(ins, steps, shfl="SHFL.UP", per_step=2):
+    """Shortest region ending at an STG.E.128 and holding exactly per_step*steps hand-off shuffles."""
     best = None
     for idx, i in enumerate(ins):
         if not (opcode(i) == "STG" and ".128" in i):
             continue
         n, j = 0, idx
-        while j >= 0 and n < 2 * steps:
-            if ins[j].replace("@!P0 ", "").startswith("SHFL.UP") or " SHFL.UP" in ins[j]:
+        while j >= 0 and n < per_step * steps:
+            if ins[j].replace("@!P0 ", "").startswith(shfl) or (" " + shfl) in ins[j]:
                 n += 1
             j -= 1
-        if n < 2 * steps:
+        if n < per_step * steps:
             continue
         # extend backwards over the instructions scheduled before the first shuffle of the block
         # until the previous control-flow instruction (the loop head / branch target)
@@ -87,9 +87,9 @@ def hot_block(ins, steps):
     return best
 
 
-def count(kernel_pat, steps, k, npair):
+def count(kernel_pat, steps, k, npair, shfl="SHFL.UP", per_step=2):
     name, ins = sass_of(kernel_pat)
-    region = hot_block(ins, steps)
+    region = hot_block(ins, steps, shfl, per_step)
     cells = steps * k * npair
     hist, pipes = {}, {"alu": 0, "fma": 0, "lsu": 0, "ctl": 0, "other": 0}
     for i in region:
@@ -109,6 +109,13 @@ def main():
            "x2": x2, "x1": x1,
            "instr_per_cell_x2": x2["instr_per_cell"], "alu_per_cell_x2": x2["alu_per_cell"], "fma_per_cell_x2": x2["fma_per_cell"],
            "instr_per_cell_x1": x1["instr_per_cell"], "alu_per_cell_x1": x1["alu_per_cell"], "fma_per_cell_x1": x1["fma_per_cell"]}
+    # gotoh2 (live aligner) kernels: forward with tie bits, score-only forward, reverse sweep (4 lane-steps x 8 columns)
+    for tag, pat, sh, per in (("g2_forward", "k2fILi8ELb0ELb1", "SHFL.UP", 2), ("g2_forward_score_only", "k2fILi8ELb0ELb0", "SHFL.UP", 2),
+                              ("g2_reverse", "k2rILi8ELb0", "SHFL.DOWN", 1)):
+        try:
+            doc[tag] = count(pat, 4, 8, 1, sh, per)
+        except Exception as e:      # a kernel without a 128-bit store in its loop (score-only) has no such block
+            doc[tag] = {"error": str(e)}
     prev = os.path.join(ROOT, "profiles", "sass_counts.json")
     if os.path.exists(prev):
         try:
@@ -120,8 +127,11 @@ def main():
             pass
     os.makedirs(os.path.dirname(prev), exist_ok=True)
     json.dump(doc, open(prev, "w"), indent=1)
-    for tag in ("x2", "x1"):
+    for tag in ("x2", "x1", "g2_forward", "g2_forward_score_only", "g2_reverse"):
         d = doc[tag]
+        if "error" in d:
+            print(tag, d["error"])
+            continue
         print("%s: %d instr / %d cells = %.2f per cell (alu %.2f, fma %.2f, lsu %.2f)" % (
             tag, d["block_instructions"], d["cells_per_block"], d["instr_per_cell"], d["alu_per_cell"], d["fma_per_cell"], d["lsu_per_cell"]))
         print("   ", sorted(d["histogram"].items(), key=lambda kv: -kv[1]))
