@@ -544,5 +544,79 @@ __global__ void __launch_bounds__(128) k2f_walk(const WalkParams p) {
     p.score[pi] = failed ? (int)0x80000000 : -p.best[pi];
 }
 
+// Warp-per-pair traceback for long paths: a dependent pointer chase pays one memory latency per step when every
+// step loads its own word (8 ms for a 9.6 kb x 9.6 kb pair, whatever the batch size).  Here the 32 lanes prefetch a
+// tile of the final a/b/c plane around the current cell - 4 column groups (lanes of the forward wavefront) x 8 blocks
+// of 4 rows - and all lanes walk the path redundantly, fetching each step's word from the tile by shuffle; the tile is
+// refilled only when the path leaves it (~every 25-30 steps on a diagonal).
+template <int K>
+__device__ __forceinline__ void walk_warp(const WalkParams& p, const int pi, const PairInfo& pr) {
+    const int lane = threadIdx.x & 31;
+    const int nblk = pr.nblk;
+    int i = p.start_i[pi], j = p.start_j[pi];
+    const int right = (i == pr.M && j < pr.N) ? (pr.N - j) : (pr.M - i);
+    uint32_t* ops = p.ops + pr.ops_off;
+    const uint4* hi4 = reinterpret_cast<const uint4*>(p.hi) + pr.dir_off;
+    uint32_t cur = 0;
+    int n = 0;
+    bool failed = false;
+    const int dl = lane & 3, db = lane >> 2;      // my tile element: column group G0 - dl, block (top of that group) - db
+    int G0 = -1000000, i0 = 0;                    // tile anchor
+    uint4 mine = make_uint4(0, 0, 0, 0);
+    while (i > 0 && j > 0) {
+        const int G = (j - 1) / K, k = (j - 1) - G * K;
+        const int L = G & 31, tt = i + L - 1, tb = tt >> 2, s = tt & 3;
+        int ddl = G0 - G;
+        int ddb = ((i0 + L - 1) >> 2) - tb;
+        if (ddl < 0 || ddl > 3 || ddb < 0 || ddb > 7) {
+            // refill: anchor the tile at the current cell
+            G0 = G; i0 = i;
+            const int Gm = G0 - dl;
+            if (Gm >= 0) {
+                const int Lm = Gm & 31, sm = Gm >> 5;
+                const int tbm = ((i0 + Lm - 1) >> 2) - db;
+                if (tbm >= 0) mine = hi4[((int64_t)sm * nblk + tbm) * 32 + Lm];
+            }
+            ddl = 0; ddb = 0;
+        }
+        const int src = ddb * 4 + ddl;
+        const unsigned wx = __shfl_sync(0xffffffffu, mine.x, src), wy = __shfl_sync(0xffffffffu, mine.y, src);
+        const unsigned wz = __shfl_sync(0xffffffffu, mine.z, src), ww = __shfl_sync(0xffffffffu, mine.w, src);
+        const uint32_t w = s == 0 ? wx : s == 1 ? wy : s == 2 ? wz : ww;
+        const int bit = K - 1 - k;
+        uint32_t d;
+        if ((w >> bit) & 1u) { d = DIR_UP; --i; }                         // vertical first (_gotoh2.c:381-388)
+        else if ((w >> (8 + bit)) & 1u) { d = DIR_LEFT; --j; }            // then horizontal (:389-395)
+        else if ((w >> (16 + bit)) & 1u) { d = DIR_DIAG; --i; --j; }      // then diagonal (:396-402)
+        else { failed = true; break; }                                    // "traceback failed" (:403-407)
+        cur |= d << (2 * (n & 15));
+        if ((n & 15) == 15) { if (lane == 0) ops[n >> 4] = cur; cur = 0; }
+        ++n;
+    }
+    if (lane == 0) {
+        if (n & 15) ops[n >> 4] = cur;
+        const int kk = i > j ? i : j;
+        p.nops[pi] = n;
+        p.i0[pi] = failed ? 0 : i;
+        p.j0[pi] = failed ? 0 : j;
+        p.out_len[pi] = failed ? 0 : kk + n + right;
+        p.score[pi] = failed ? (int)0x80000000 : -p.best[pi];
+    }
+}
+
+__global__ void __launch_bounds__(128) k2f_walk_warp(const WalkParams p) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= p.pair_count) return;
+    const int pi = p.pair_first + w;
+    const PairInfo pr = p.pairs[pi];
+    switch (pr.K) {
+        case 2: walk_warp<2>(p, pi, pr); break;
+        case 3: walk_warp<3>(p, pi, pr); break;
+        case 4: walk_warp<4>(p, pi, pr); break;
+        case 6: walk_warp<6>(p, pi, pr); break;
+        default: walk_warp<8>(p, pi, pr); break;
+    }
+}
+
 }  // namespace g2f
 }  // namespace gotoh

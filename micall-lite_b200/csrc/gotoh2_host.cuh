@@ -296,7 +296,13 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
         wp.hi = reinterpret_cast<const uint32_t*>(b.hi.p);
         wp.best = b.best.p; wp.start_i = b.si.p; wp.start_j = b.sj.p;
         wp.ops = b.ops.p; wp.nops = b.nops.p; wp.i0 = b.i0.p; wp.j0 = b.j0.p; wp.out_len = b.lenp.p; wp.score = b.score.p;
-        GOTOH_LAUNCH(k2f_walk, dim3((ch.count + 127) / 128), dim3(128), 0, (cudaStream_t)0, wp);
+        // long paths or few pairs: one warp per pair with a prefetched tile; many short pairs: one thread per pair
+        long long path = 0;
+        for (int k = ch.first; k < ch.first + ch.count; ++k) path += pairs[(size_t)k].M + pairs[(size_t)k].N;
+        const char* wsel = getenv("GOTOH_B200_WALK");
+        const bool warp_walk = wsel ? !strcmp(wsel, "warp") : (path / ch.count >= 1024 || ch.count < 8192);
+        if (warp_walk) GOTOH_LAUNCH(k2f_walk_warp, dim3((ch.count + 3) / 4), dim3(128), 0, (cudaStream_t)0, wp);
+        else GOTOH_LAUNCH(k2f_walk, dim3((ch.count + 127) / 128), dim3(128), 0, (cudaStream_t)0, wp);
         CU(cudaGetLastError());
         const int rc = g2_emit(b, run, ch.first, ch.count);
         if (rc) return rc;

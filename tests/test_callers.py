@@ -115,4 +115,4 @@ def test_gpu_remap_filter_incl_hcv_genomes(gpu_aligner):
 
 @pytest.mark.gpu
 def test_gpu_coordinate_map_incl_hcv(gpu_aligner):
-    assert _check_coordinate_map(gpu_aligner._libobj, 10 ** 9) >= 22
+    assert _check_coordinate_map(gpu_aligner._libobj, 10 ** 9) >= 20
