@@ -122,7 +122,7 @@ void gotoh_b200_plan_destroy(gotoh_b200_plan* plan);
  *   6 pairs on the 32-bit path          7 number of arena chunks per run */
 int64_t gotoh_b200_plan_stat(const gotoh_b200_plan* plan, int32_t what);
 
-/* gotoh_b200_align_batch keeps two workspaces (device buffers, pinned staging, a stream) per
+/* gotoh_b200_align_batch keeps three workspaces (device buffers, pinned staging, a stream) per
  * device alive between calls so that small calls do not pay for cudaMalloc; this frees them. */
 void gotoh_b200_release_cache(void);
 

@@ -12,6 +12,8 @@
 #include "gotoh_intpeak.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -122,6 +124,7 @@ struct Workspace {
     bool ready = false;
     cudaStream_t stream = 0;
     cudaEvent_t ev[4] = {0, 0, 0, 0};
+    int trace_slab = -1;       // GOTOH_B200_TRACE: slab whose events ev[0..2] are pending
     int sm_count = 1;
     // device
     DevBuf<uint8_t> d_ref_raw, d_ref_cls, d_qry, d_out_ref, d_out_qry;
@@ -261,6 +264,11 @@ void parallel_for(int64_t n, int threads, F fn) {
     for (auto& x : th) x.join();
 }
 
+// GOTOH_B200_TRACE=1: per-slab host timings of the one-shot call on stderr (diagnostics only)
+inline bool trace_on() { static const bool on = getenv("GOTOH_B200_TRACE") != nullptr; return on; }
+inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+thread_local double g_trace_phase[8];
+
 int host_threads(int64_t bytes) {
     if (bytes < (1 << 20)) return 1;
     const char* e = getenv("GOTOH_B200_HOST_THREADS");
@@ -330,6 +338,8 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     CU(cudaSetDevice(ws->device));
     pl->cells = 0; pl->h2d_bytes = 0; pl->pairs_x1 = pl->pairs_x2 = 0;
 
+    double tph = now_ms();
+    auto phase = [&](int k) { const double t = now_ms(); g_trace_phase[k] += t - tph; tph = t; };
     // ---- references used by this range: trim, degap, validate, classes ------------------
     std::vector<int32_t> ref_local;
     std::vector<int64_t> used_refs;
@@ -383,6 +393,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         ref_len[u] = m;
     }
 
+    phase(0);
     // ---- queries, pass 1 (parallel): trim span, validate, length after degap, byte presence ----
     std::vector<HostPair> hp((size_t)n);
     const int64_t qbytes_in = qry_off[pair_end] - qry_off[pair_begin];
@@ -441,6 +452,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         for (int c = 0; c < 128; ++c) qry_present[c] |= te.present[c];
         pl->cells += te.cells;
     }
+    phase(1);
     // ---- pass 2 (parallel): packed positions + copy ------------------------------------------
     int64_t qtotal = 0;
     std::vector<int64_t> span((size_t)n);
@@ -458,6 +470,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         }
     });
 
+    phase(2);
     // ---- classes of reference bytes, compact table, score range ----------------------------
     // A class is a distinct reference byte - or, in references that contain "$$$", a distinct
     // (byte, rmask) where rmask says which of the three stop-codon bonus rules (gotoh.cpp:324-344)
@@ -505,6 +518,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     }
     if (any_dollar3) maxT += 18;                   // up to three +6 bonuses on one cell
 
+    phase(3);
     // ---- choose the path per pair, form warp tasks -------------------------------------------
     // Vec16 (two alignments per warp) needs: single strip (N <= 32*Kmax), same reference for both
     // halves, and the int16 range proof.  Everything else runs Vec32.
@@ -549,8 +563,10 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
             if (all) { R = cand; break; }
         }
     }
+    phase(4);
     std::sort(elig.begin(), elig.end());
     std::sort(wide.begin(), wide.end());
+    phase(5);
 
     CU(ws->h_pairs.ensure((size_t)n));
     CU(ws->h_tasks.ensure((size_t)n));
@@ -611,6 +627,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     pl->pair_base = pair_begin;
     pl->n_pairs = n;
 
+    phase(6);
     // ---- device buffers (grow-only, reused across plans on this workspace) ---------------------
     CU(ws->d_ref_raw.ensure(ref_total));
     CU(ws->d_ref_cls.ensure(ref_total));
@@ -695,6 +712,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     CU(h2d(ws->d_table4.p, h_table4, (size_t)pl->ncls * 136 * sizeof(int32_t)));
     CU(h2d(ws->d_pairs.p, pairs, (size_t)n * sizeof(PairInfo)));
     CU(h2d(ws->d_tasks.p, tasks, n_tasks * sizeof(Task)));
+    phase(7);
     return GOTOH_B200_OK;
 }
 
@@ -806,10 +824,13 @@ int check_common(const void* ref_bytes, const int64_t* ref_off, int64_t n_refs, 
     return GOTOH_B200_OK;
 }
 
-// ---- cached per-device contexts for the one-shot call: two workspaces = two slabs in flight ----
+// ---- cached per-device contexts for the one-shot call: four workspaces = four slabs in flight ----
+// (two being packed by the two builder threads, one in its kernels, one copying back; with two, the host could not start packing
+// slab s+1 before slab s-1 had finished its D2H and the kernels idled ~30 % of the time - measured on B200)
+enum { NWS = 4, NBUILD = 2 };
 struct DeviceCtx {
     std::mutex mu;
-    Workspace ws[2];
+    Workspace ws[NWS];
 };
 std::mutex g_ctx_mu;
 DeviceCtx* g_ctx[64] = {nullptr};
@@ -821,8 +842,8 @@ DeviceCtx* ctx_for(int dev) {
 }
 
 // One device's share [lo, hi) of a one-shot call: cut into slabs of bounded arena size, each slab is a
-// self-contained plan on one of two workspaces (streams), so host packing of slab s+1 and the D2H of
-// slab s overlap the kernels of the slab in between.
+// self-contained plan on one of three workspaces (streams), so host packing of slab s+1 and the D2H of
+// slab s-1 overlap the kernels of slab s.
 int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
                      const int32_t* ref_idx, const uint8_t* qry_bytes, const int64_t* qry_off,
                      int64_t lo, int64_t hi, int32_t gip, int32_t gep, int32_t term, int32_t matrix_id,
@@ -830,24 +851,26 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     DeviceCtx* ctx = ctx_for(dev);
     if (!ctx) return fail(GOTOH_B200_ENOMEM, "out of host memory");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    for (int w = 0; w < 2; ++w) { const int rc = ctx->ws[w].init(dev); if (rc) return rc; }
+    for (int w = 0; w < NWS; ++w) { const int rc = ctx->ws[w].init(dev); if (rc) return rc; }
     CU(cudaSetDevice(dev));
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const int64_t cached = (int64_t)(ctx->ws[0].d_dir.cap + ctx->ws[1].d_dir.cap) * 16;
-    int64_t slab_budget = std::min<int64_t>(((int64_t)free_b + cached) / 5, (int64_t)24 << 30);
+    int64_t cached = 0;
+    for (int w = 0; w < NWS; ++w) cached += (int64_t)ctx->ws[w].d_dir.cap * 16;
+    // small slabs keep the pipeline's fill and drain short (first packing, last D2H); 3 GB of arena = ~16 k reads
+    int64_t slab_budget = std::min<int64_t>(((int64_t)free_b + cached) / (NWS + 2), (int64_t)3 << 30);
     slab_budget = std::max<int64_t>(slab_budget, (int64_t)256 << 20);
     if (getenv("GOTOH_B200_SLAB_MB")) slab_budget = (int64_t)atoll(getenv("GOTOH_B200_SLAB_MB")) << 20;   // tests
-    gotoh_b200_plan plans[2];
-    for (int w = 0; w < 2; ++w) {
+    gotoh_b200_plan plans[NWS];
+    for (int w = 0; w < NWS; ++w) {
         plans[w].ws = &ctx->ws[w];
         plans[w].gip = gip; plans[w].gep = gep; plans[w].term = term ? 1 : 0; plans[w].matrix = matrix_id;
         plans[w].arena_budget_bytes = slab_budget;
     }
-    int rc = GOTOH_B200_OK;
-    int slab = 0;
-    for (int64_t k = lo; k < hi && !rc;) {
-        // slab = as many consecutive pairs as fit the arena estimate ((M+40)*64 B per strip per pair)
+    // slab = as many consecutive pairs as fit the arena estimate ((M+40)*64 B per strip per pair).  (Ramping the slab
+    // size up and down to shorten the pipeline's fill and drain was tried and measured slower on B200 than equal slabs.)
+    std::vector<int64_t> cuts(1, lo);
+    for (int64_t k = lo; k < hi;) {
         int64_t est = 0, e = k;
         while (e < hi) {
             const int64_t r = ref_idx ? ref_idx[e] : e;
@@ -858,20 +881,68 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
             est += need;
             ++e;
         }
-        gotoh_b200_plan* pl = &plans[slab & 1];
-        // the workspace's previous slab (two slabs ago) must have drained before its staging is reused
-        if (cudaStreamSynchronize(pl->ws->stream) != cudaSuccess) { rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed"); break; }
-        try {
-            rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, k, e, out_off);
-        } catch (const std::bad_alloc&) {
-            rc = fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
-        }
-        if (!rc) rc = plan_run(pl, false, nullptr, nullptr);
-        if (!rc) rc = plan_fetch(pl, out_ref, out_qry, out_len, out_score);
+        cuts.push_back(e);
         k = e;
-        ++slab;
     }
-    for (int w = 0; w < 2; ++w) {
+    const int nslabs = (int)cuts.size() - 1;
+    if (trace_on()) { cudaEventRecord(ctx->ws[0].ev[3], ctx->ws[0].stream); cudaEventSynchronize(ctx->ws[0].ev[3]); for (int w = 0; w < NWS; ++w) ctx->ws[w].trace_slab = -1; }
+    // Two builder threads pack alternate slabs (each owns half of the workspaces), so the host's packing rate is
+    // not the pipeline's bottleneck: per slab the host needs about as long as the kernels (measured on B200).
+    int builders = getenv("GOTOH_B200_BUILDERS") ? atoi(getenv("GOTOH_B200_BUILDERS")) : NBUILD;
+    builders = std::max(1, std::min(std::min(builders, (int)NBUILD), nslabs));
+    std::vector<int> rcs((size_t)builders, 0);
+    std::vector<std::string> msgs((size_t)builders);
+    std::atomic<int> failed(0);
+    auto builder = [&](int b) {
+        if (cudaSetDevice(dev) != cudaSuccess) { rcs[(size_t)b] = GOTOH_B200_ECUDA; msgs[(size_t)b] = "cudaSetDevice failed"; failed = 1; return; }
+        int mine = 0;
+        for (int slab = b; slab < nslabs && !failed.load(); slab += builders, ++mine) {
+            // builder b owns workspaces b, b+builders, ...; its previous slab on that workspace must have drained
+            const int per = NWS / builders;
+            gotoh_b200_plan* pl = &plans[b + builders * (mine % per)];
+            int rc = GOTOH_B200_OK;
+            const double t_a = now_ms();
+            if (cudaStreamSynchronize(pl->ws->stream) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed");
+            if (trace_on() && pl->ws->trace_slab >= 0) {
+                float k0 = 0, k1 = 0, d1 = 0;
+                cudaEventElapsedTime(&k0, ctx->ws[0].ev[3], pl->ws->ev[0]);
+                cudaEventElapsedTime(&k1, ctx->ws[0].ev[3], pl->ws->ev[1]);
+                cudaEventElapsedTime(&d1, ctx->ws[0].ev[3], pl->ws->ev[2]);
+                fprintf(stderr, "[gotoh_b200] gpu timeline slab %d: kernels %.2f .. %.2f ms, d2h done %.2f ms\n", pl->ws->trace_slab, k0, k1, d1);
+                pl->ws->trace_slab = -1;
+            }
+            const double t_b = now_ms();
+            for (double& x : g_trace_phase) x = 0;
+            if (!rc) {
+                try {
+                    rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, cuts[(size_t)slab], cuts[(size_t)slab + 1], out_off);
+                } catch (const std::bad_alloc&) {
+                    rc = fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
+                }
+            }
+            const double t_c = now_ms();
+            if (trace_on() && !rc) cudaEventRecord(pl->ws->ev[0], pl->ws->stream);
+            if (!rc) rc = plan_run(pl, false, nullptr, nullptr);
+            if (trace_on() && !rc) cudaEventRecord(pl->ws->ev[1], pl->ws->stream);
+            if (!rc) rc = plan_fetch(pl, out_ref, out_qry, out_len, out_score);
+            if (trace_on() && !rc) { cudaEventRecord(pl->ws->ev[2], pl->ws->stream); pl->ws->trace_slab = slab; }
+            if (trace_on())
+                fprintf(stderr, "[gotoh_b200] dev %d builder %d slab %d pairs %lld: wait %.1f ms, build %.1f ms (refs %.1f pass1 %.1f pass2 %.1f cls %.1f path %.1f sort %.1f tasks %.1f alloc+h2d %.1f), enqueue %.1f ms\n",
+                        dev, b, slab, (long long)(cuts[(size_t)slab + 1] - cuts[(size_t)slab]), t_b - t_a, t_c - t_b, g_trace_phase[0], g_trace_phase[1],
+                        g_trace_phase[2], g_trace_phase[3], g_trace_phase[4], g_trace_phase[5], g_trace_phase[6], g_trace_phase[7], now_ms() - t_c);
+            if (rc) { rcs[(size_t)b] = rc; msgs[(size_t)b] = g_err; failed = 1; return; }
+        }
+    };
+    if (builders == 1) builder(0);
+    else {
+        std::vector<std::thread> th;
+        for (int b = 0; b < builders; ++b) th.emplace_back(builder, b);
+        for (auto& t : th) t.join();
+    }
+    int rc = GOTOH_B200_OK;
+    for (int b = 0; b < builders; ++b)
+        if (rcs[(size_t)b] && !rc) rc = fail(rcs[(size_t)b], "%s", msgs[(size_t)b].c_str());
+    for (int w = 0; w < NWS; ++w) {
         const cudaError_t e = cudaStreamSynchronize(ctx->ws[w].stream);
         if (e != cudaSuccess && !rc) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
     }
@@ -948,8 +1019,7 @@ extern "C" void gotoh_b200_release_cache(void) {
     for (int d = 0; d < 64; ++d)
         if (g_ctx[d]) {
             std::lock_guard<std::mutex> lk2(g_ctx[d]->mu);
-            g_ctx[d]->ws[0].release();
-            g_ctx[d]->ws[1].release();
+            for (int w = 0; w < NWS; ++w) g_ctx[d]->ws[w].release();
         }
 }
 
