@@ -68,15 +68,6 @@ struct Params {
     uint32_t* counter_r;
 };
 
-__device__ __forceinline__ int ld_volatile(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
-__device__ __forceinline__ void st_volatile(int32_t* p, int v) { *reinterpret_cast<volatile int32_t*>(p) = v; }
-
-#ifdef GOTOH_SIMT_EMU
-template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return *p; }
-#else
-template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
-#endif
-
 template <int K>
 struct Smem {
     enum { K4 = (K + 3) / 4 };

@@ -230,10 +230,17 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
             const int K = gi < 5 ? kK[gi] : 8;
             const bool multi = (gi == 5);
             const int t0 = (int)tasks.size();
-            for (int k = ch.first; k < ch.first + ch.count; ++k) {
-                if (pairs[(size_t)k].K != K || (extra[(size_t)k].nstrips > 1) != multi) continue;
-                for (int s = 0; s < extra[(size_t)k].nstrips; ++s) tasks.push_back({k, s});
-            }
+            // strip-major order (strip 0 of every pair, then strip 1, ...): a warp that claims (pair, s) finds (pair, s-1)
+            // far ahead instead of spinning right behind a producer that has just started; a producer still precedes its
+            // consumer in claim order (forward) and in reversed order (reverse sweep), which rules out deadlock
+            int max_ns = 0;
+            for (int k = ch.first; k < ch.first + ch.count; ++k)
+                if (pairs[(size_t)k].K == K && (extra[(size_t)k].nstrips > 1) == multi) max_ns = std::max(max_ns, extra[(size_t)k].nstrips);
+            for (int s = 0; s < max_ns; ++s)
+                for (int k = ch.first; k < ch.first + ch.count; ++k) {
+                    if (pairs[(size_t)k].K != K || (extra[(size_t)k].nstrips > 1) != multi || s >= extra[(size_t)k].nstrips) continue;
+                    tasks.push_back({k, s});
+                }
             if ((int)tasks.size() > t0) groups.push_back({K, multi, t0, (int)tasks.size() - t0});
         }
         CU(cudaMemcpy(b.tasks.p, tasks.data(), tasks.size() * sizeof(StripTask), cudaMemcpyHostToDevice));

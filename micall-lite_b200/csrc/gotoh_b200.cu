@@ -133,6 +133,9 @@ struct Workspace {
     DevBuf<int32_t> d_table4, d_score, d_end_i, d_end_j, d_nops, d_i0, d_j0, d_len_plan, d_out_len, d_out_score;
     DevBuf<uint4> d_dir;
     DevBuf<int2> d_bnd;
+    DevBuf<Task> d_stasks;          // strip tasks of the dataflow kernel
+    DevBuf<int32_t> d_flow;         // [3][slots]: progress, last-row partial score, its column
+    PinBuf<Task> h_stasks;
     DevBuf<uint32_t> d_ops, d_counter;
     // pinned staging
     PinBuf<uint8_t> h_ref_raw, h_ref_cls, h_qry;
@@ -159,7 +162,7 @@ struct Workspace {
         d_ref_raw.release(); d_ref_cls.release(); d_qry.release(); d_out_ref.release(); d_out_qry.release();
         d_pairs.release(); d_tasks.release(); d_table4.release(); d_score.release(); d_end_i.release();
         d_end_j.release(); d_nops.release(); d_i0.release(); d_j0.release(); d_len_plan.release();
-        d_out_len.release(); d_out_score.release(); d_dir.release(); d_bnd.release(); d_ops.release();
+        d_out_len.release(); d_out_score.release(); d_dir.release(); d_bnd.release(); d_stasks.release(); d_flow.release(); h_stasks.release(); d_ops.release();
         d_counter.release();
         h_ref_raw.release(); h_ref_cls.release(); h_qry.release(); h_pairs.release(); h_tasks.release(); h_table4.release();
         for (int i = 0; i < 4; ++i) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = 0; }
@@ -175,6 +178,8 @@ struct Launch {
     int task_first, task_count;
     int rebase_mask;
     int multi_strip;
+    int nslots = 0;        // multi-strip launches: (pair, strip) slots = strip tasks of the dataflow kernel
+    int stask_first = 0;   // first strip task in d_stasks
 };
 struct Chunk {
     std::vector<Launch> launches;
@@ -196,6 +201,8 @@ struct gotoh_b200_plan {
     int64_t out_base = 0, out_bytes = 0;   // caller's out_off range covered by this plan
     int64_t pair_base = 0;                 // first caller pair index
     int64_t bnd_stride = 0;
+    int flow_slots = 0;                    // > 0: the strip-dataflow kernel can run (boundary columns allocated)
+    int64_t n_stasks = 0;
     int64_t arena_budget_bytes = 0;        // 0: 80 % of free memory
     // stats
     int64_t cells = 0, h2d_bytes = 0, d2h_bytes = 0, arena_bytes = 0, pairs_x2 = 0, pairs_x1 = 0;
@@ -306,6 +313,20 @@ int launch_forward_cta(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
     int grid = std::max(1, std::min(ntasks, ws->sm_count * ctas_per_sm));
     grid = (int)std::min<long long>(grid, std::max<long long>(1, (long long)ws->d_bnd.cap / (2 * pl->bnd_stride)));
     GOTOH_LAUNCH((k_forward_cta<8>), dim3(grid), dim3(FWD_WARPS * 32), smem, ws->stream, fp);
+    CU(cudaGetLastError());
+    return GOTOH_B200_OK;
+}
+
+// K2 (default): strip dataflow, one warp per (pair, strip)
+int launch_forward_flow(const gotoh_b200_plan* pl, const FwdParams& fp, int ntasks) {
+    const Workspace* ws = pl->ws;
+    const size_t per_warp = FwdSmem<Vec32, 8>::per_warp(pl->ncls);
+    const size_t smem = per_warp * FWD_WARPS;
+    if (smem > 220 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
+    CU(cudaFuncSetAttribute(k_forward_flow<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(GOTOH_MIN_CTAS, (200 * 1024) / std::max<size_t>(smem, 1)));
+    const int grid = std::max(1, std::min((ntasks + FWD_WARPS - 1) / FWD_WARPS, ws->sm_count * ctas_per_sm));
+    GOTOH_LAUNCH((k_forward_flow<8>), dim3(grid), dim3(FWD_WARPS * 32), smem, ws->stream, fp);
     CU(cudaGetLastError());
     return GOTOH_B200_OK;
 }
@@ -681,6 +702,12 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         }
         cur.launches.back().task_count++;
         const Task& tk = tasks[t];
+        if (m.multi) {
+            // strip dataflow: this pair's strips take the next slots of its launch
+            const PairInfo& pp = pairs[tk.pair_a];
+            pairs[tk.pair_a].pad1 = cur.launches.back().nslots;
+            cur.launches.back().nslots += (pp.N + 32 * pp.K - 1) / (32 * pp.K);
+        }
         pairs[tk.pair_a].dir_off = used;
         if (tk.pair_b >= 0) pairs[tk.pair_b].dir_off = used;
         used += m.arena;
@@ -689,6 +716,46 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         pair_cursor += np;
     }
     flush();
+    // strip tasks of the multi-strip launches: (pair, strip) in pair-major, strip-ascending order
+    {
+        size_t total = 0;
+        int max_slots = 0;
+        for (Chunk& c : pl->chunks)
+            for (Launch& L : c.launches)
+                if (L.multi_strip) { L.stask_first = (int)total; total += (size_t)L.nslots; max_slots = std::max(max_slots, L.nslots); }
+        if (total) {
+            CU(ws->h_stasks.ensure(total));
+            CU(ws->d_stasks.ensure(total));
+            CU(ws->d_flow.ensure((size_t)max_slots * 3 + 3));
+            size_t at = 0;
+            for (const Chunk& c : pl->chunks)
+                for (const Launch& L : c.launches) {
+                    if (!L.multi_strip) continue;
+                    // strip-major: strip 0 of every pair, then strip 1, ... - a warp that claims (pair, s) then finds
+                    // (pair, s-1) far ahead (or finished) instead of spinning 64 rows behind a producer that has just
+                    // started; a producer still precedes its consumer in claim order, which is what rules out deadlock
+                    int max_ns = 0;
+                    for (int t = L.task_first; t < L.task_first + L.task_count; ++t) {
+                        const PairInfo& pp = pairs[tasks[t].pair_a];
+                        max_ns = std::max(max_ns, (pp.N + 32 * pp.K - 1) / (32 * pp.K));
+                    }
+                    for (int sidx = 0; sidx < max_ns; ++sidx)
+                        for (int t = L.task_first; t < L.task_first + L.task_count; ++t) {
+                            const PairInfo& pp = pairs[tasks[t].pair_a];
+                            if (sidx >= (pp.N + 32 * pp.K - 1) / (32 * pp.K)) continue;
+                            ws->h_stasks.p[at].pair_a = tasks[t].pair_a; ws->h_stasks.p[at].pair_b = sidx; ++at;
+                        }
+                }
+            pl->flow_slots = max_slots;
+            // one boundary column per slot (d_bnd is also what the warp-serial / CTA kernels use)
+            const char* pin = getenv("GOTOH_B200_LONG");
+            if (!pin || pin[0] == 'f') {
+                cudaError_t e = ws->d_bnd.ensure((size_t)max_slots * (size_t)pl->bnd_stride + 16);
+                if (e != cudaSuccess) { (void)cudaGetLastError(); pl->flow_slots = 0; }     // fall back to the warp-serial kernel
+            }
+            pl->n_stasks = (int64_t)total;
+        }
+    }
     pl->n_launches = 0;
     for (const Chunk& c : pl->chunks) pl->n_launches += (int)c.launches.size() + 2;
     {
@@ -712,6 +779,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     CU(h2d(ws->d_table4.p, h_table4, (size_t)pl->ncls * 136 * sizeof(int32_t)));
     CU(h2d(ws->d_pairs.p, pairs, (size_t)n * sizeof(PairInfo)));
     CU(h2d(ws->d_tasks.p, tasks, n_tasks * sizeof(Task)));
+    if (pl->n_stasks) CU(h2d(ws->d_stasks.p, ws->h_stasks.p, (size_t)pl->n_stasks * sizeof(Task)));
     phase(7);
     return GOTOH_B200_OK;
 }
@@ -754,10 +822,21 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
                 // GCUPS; below ~2 pairs per resident CTA the CTA form is ahead).  GOTOH_B200_LONG=cta|warp
                 // pins the choice (tests, benchmarks).
                 const char* pin = getenv("GOTOH_B200_LONG");
-                bool cta = L.task_count < ws->sm_count * GOTOH_MIN_CTAS * 2;
-                if (pin) cta = (pin[0] == 'c');
-                rc = cta ? launch_forward_cta(pl, fp, L.task_count) : -1;
-                if (rc == -1) rc = launch_forward_k<Vec32, 8, true>(pl, fp, L.task_count);
+                // (with very many reference classes the 4-warp CTA's profiles exceed shared memory: warp-serial kernel then)
+                const bool flow = pl->flow_slots > 0 && (!pin || pin[0] == 'f') &&
+                                  FwdSmem<Vec32, 8>::per_warp(pl->ncls) * FWD_WARPS <= 200 * 1024;
+                if (flow) {
+                    // K2 default: strip dataflow - every (pair, strip) is a warp task, any number of pairs fills the GPU
+                    CU(cudaMemsetAsync(ws->d_flow.p, 0, (size_t)L.nslots * sizeof(int32_t), ws->stream));
+                    fp.tasks = ws->d_stasks.p; fp.task_first = L.stask_first; fp.task_count = L.nslots;
+                    fp.prog = ws->d_flow.p; fp.part_best = ws->d_flow.p + pl->flow_slots; fp.part_j = ws->d_flow.p + 2 * (size_t)pl->flow_slots;
+                    rc = launch_forward_flow(pl, fp, L.nslots);
+                } else {
+                    bool cta = L.task_count < ws->sm_count * GOTOH_MIN_CTAS * 2;
+                    if (pin) cta = (pin[0] == 'c');
+                    rc = cta ? launch_forward_cta(pl, fp, L.task_count) : -1;
+                    if (rc == -1) rc = launch_forward_k<Vec32, 8, true>(pl, fp, L.task_count);
+                }
             }
             if (rc) return rc;
         }

@@ -90,6 +90,10 @@ struct FwdParams {
     int32_t* end_i;
     int32_t* end_j;
     uint32_t* work_counter;     // dynamic task scheduler
+    // strip dataflow (k_forward_flow): tasks are (pair_a = pair, pair_b = strip); slot = pairs[pair].pad1 + strip
+    int32_t* prog;              // rows published per slot
+    int32_t* part_best;         // last-row partial maximum per slot
+    int32_t* part_j;
 };
 
 // ------------------------------------------------------------------------------------
@@ -188,14 +192,27 @@ __device__ __forceinline__ void gotoh_pause() {
 #endif
 }
 
+// Cross-warp hand-over through global memory (strip dataflow): flags are polled with volatile loads, the data
+// behind a flag is read with ld.global.cg (L2; L1 is not coherent between SMs).
+__device__ __forceinline__ int ld_volatile(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+__device__ __forceinline__ void st_volatile(int32_t* p, int v) { *reinterpret_cast<volatile int32_t*>(p) = v; }
+#ifdef GOTOH_SIMT_EMU
+template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return *p; }
+#else
+template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
+#endif
+
 // MODE 0: the query fits one strip.  MODE 1: one warp walks the strips one after another, boundary
 // columns through global memory.  MODE 2 (K2, long pairs): the 4 warps of a CTA work on adjacent strips
 // of ONE pair at the same time, each ~64 rows behind its left neighbour - an anti-diagonal wavefront
-// across the CTA - handing boundary columns over through shared-memory rings.
+// across the CTA - handing boundary columns over through shared-memory rings.  MODE 3 (strip dataflow): every
+// (pair, strip) is its own warp task; strip s publishes its last column to global memory every 32 rows and strip
+// s+1 - on any warp of any CTA - follows ~64 rows behind.  Tasks are claimed from an atomic counter in (pair, strip)
+// order, so a strip's producer is always claimed earlier and is running: the spin-waits cannot deadlock.
 template <class V, int K, int MODE>
 struct Wave {
     typedef typename V::T T;
-    enum { K4 = (K + 3) / 4, STEPS = V::STEPS, NP = V::NPAIR, MULTI = (MODE != 0), CTA = (MODE == 2), XR = 256 };
+    enum { K4 = (K + 3) / 4, STEPS = V::STEPS, NP = V::NPAIR, MULTI = (MODE != 0), CTA = (MODE == 2), FLOW = (MODE == 3), XR = 256 };
 
     // ---- per-task / per-strip constants --------------------------------------------------
     int lane, M, Na, Nb, j0, strip, gep, g4, rebase_mask, smin_m1;
@@ -219,6 +236,9 @@ struct Wave {
     // full-length column in global memory (pub only, no back-pressure: warp 0 is always ahead of it).
     int2* col;
     bool in_col, out_col;
+    // MODE 3: rows published by the producer of my left boundary / by me
+    const int32_t* prog_in;
+    int32_t* prog_out;
     T c_up, c_sl0, c_q0, c_g4, c_g4_lane0;
     unsigned keep, inj_s, inj_q;   // lane-0 injection of column 0
     T Uq[K];
@@ -276,7 +296,7 @@ struct Wave {
                 __syncwarp();
                 const int row = t + lane;                   // lane 0 is at row t+l at step t+l
                 int2 b = make_int2(0, 0);
-                if (row >= 1 && row <= M) b = bnd_in[row];
+                if (row >= 1 && row <= M) b = FLOW ? ld_cg(&bnd_in[row]) : bnd_in[row];
                 ring[(((t - 1) >> 5) & 1) * 32 + lane] = b;
                 __syncwarp();
             }
@@ -418,9 +438,22 @@ struct Wave {
                 __syncwarp();
             }
         }
+        if (FLOW && strip > 0 && ((t0 - 1) & 31) == 0) {
+            // lane 0 consumes rows t0 .. t0+31 of the left strip's last column during the next 32 steps
+            if (lane == 0) {
+                const int need = min(t0 + 31, M);
+                while (ld_volatile(prog_in) < need) gotoh_pause();
+                __threadfence();
+            }
+            __syncwarp();
+        }
 #pragma unroll
         for (int s = 0; s < STEPS; ++s) step<SLOW>(tb * STEPS + s + 1, s);
         *dst = dwords;   // one coalesced 512-byte store per warp per STEPS lane-steps
+        if (FLOW && !last_strip && (hi & 31) == 0 && hi - 31 >= 1 && hi - 31 < M) {
+            __syncwarp();
+            if (lane == 31) { __threadfence(); st_volatile(prog_out, hi - 31); }
+        }
         if (CTA && !last_strip) {
             __syncwarp();
             if (lane == 31) {
@@ -588,6 +621,139 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
                     if (lr_best_b > best_b) { p.score[task.pair_b] = lr_best_b; p.end_i[task.pair_b] = M; p.end_j[task.pair_b] = lr_j_b; }
                     else { p.score[task.pair_b] = best_b; p.end_i[task.pair_b] = bi_b; p.end_j[task.pair_b] = Nb; }
                 }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K2  long pairs as strip dataflow: one warp per (pair, strip), strips of a pair pipelined across the whole grid
+// ------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_flow(const FwdParams p) {
+    typedef Vec32 V;
+    typedef Wave<V, K, 3> W;
+    enum { K4 = W::K4, STEPS = V::STEPS };
+    GOTOH_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* my_smem = smem_raw + (size_t)warp * FwdSmem<V, K>::per_warp(p.ncls);
+    uint4* prof = reinterpret_cast<uint4*>(my_smem);
+    W w;
+    w.lane = lane;
+    w.gep = p.gep;
+    w.g4 = 4 * p.gep;
+    w.rebase_mask = p.rebase_mask;
+    w.smin_m1 = p.smin_m1;
+    w.four = p.four;
+    w.prof_lane = prof + lane;
+    w.ring = reinterpret_cast<int2*>(my_smem + (size_t)p.ncls * K4 * 32 * 16);
+    const int u4 = -4 * p.gip;
+    w.c_up = V::both(u4 + 1);
+    w.c_sl0 = V::both(u4);
+    w.c_q0 = V::both(2 * u4 + 2);
+    w.c_g4 = V::both(w.g4);
+    w.c_g4_lane0 = lane == 0 ? w.c_g4 : V::both(0);
+    w.keep = (p.four >> 2) - (lane == 0 ? 1u : 0u);
+    w.inj_s = lane == 0 ? V::raw(w.c_sl0) : 0u;
+    w.inj_q = lane == 0 ? V::raw(w.c_q0) : 0u;
+
+    for (;;) {
+        unsigned tsk = 0;
+        if (lane == 0) tsk = atomicAdd(p.work_counter, 1u);
+        tsk = __shfl_sync(0xffffffffu, tsk, 0);
+        if (tsk >= (unsigned)p.task_count) break;
+        const Task task = p.tasks[p.task_first + tsk];
+        const PairInfo pa = p.pairs[task.pair_a];
+        const int strip = task.pair_b;
+        const int M = pa.M, Na = pa.N;
+        const int nstrips = (Na + 32 * K - 1) / (32 * K);
+        const int nblk = pa.nblk;
+        const int slot = pa.pad1 + strip;
+        const uint8_t* qa = p.qry + pa.qry_pos;
+        const int j0 = (strip * 32 + lane) * K;
+        w.M = M; w.Na = Na; w.Nb = Na;
+        w.cls = p.ref_cls + pa.ref_pos;
+        w.lr_best_a = w.lr_best_b = -2147483647;
+        w.lr_j_a = w.lr_j_b = 0;
+        w.strip = strip;
+        w.j0 = j0;
+        w.last_strip = (strip == nstrips - 1);
+        w.bnd_in = p.bnd + (int64_t)(slot - 1) * p.bnd_stride;
+        w.bnd_out = p.bnd + (int64_t)slot * p.bnd_stride;
+        w.prog_in = p.prog + slot - 1;
+        w.prog_out = p.prog + slot;
+
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) w.Uq[k] = V::both((j0 + k) < Na ? u4 + 2 : 3);
+        int cm_a[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) cm_a[k] = p.has_dollar ? stop_mask(qa, Na, j0 + k + 1) : 0;
+        for (int c = 0; c < p.ncls; ++c) {
+            const int32_t* trow = p.table4 + c * 128;
+            const int32_t* brow = p.bonus4 + c * 8;
+#pragma unroll
+            for (int kq = 0; kq < K4; ++kq) {
+                unsigned e[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = kq * 4 + kk;
+                    const int ja = j0 + k;
+                    int ea = u4;
+                    if (k < K && ja < Na) ea = trow[qa[ja]] + (p.has_dollar ? brow[cm_a[k]] : 0);
+                    e[kk] = (unsigned)ea;
+                }
+                prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
+            }
+        }
+        __syncwarp();
+        w.sendS = V::both(0);
+        w.sendQ = V::both(0);
+        w.dwords = make_uint4(0, 0, 0, 0);
+        w.row0_init();
+        w.next_cls = w.cls[-lane];
+
+        uint4* dst = p.dir + pa.dir_off + (int64_t)strip * nblk * 32 + lane;
+        for (int tb = 0; tb < nblk; ++tb, dst += 32) {
+            const int t0 = tb * STEPS + 1, hi = t0 + STEPS - 1;
+            const bool slow = (t0 <= 31) || (hi >= M);
+            if (slow) w.template block<true>(tb, dst);
+            else w.template block<false>(tb, dst);
+        }
+        // last row of this strip: (score, j) with larger j winning ties (gotoh.cpp:399-403)
+        int lr_best = w.lr_best_a, lr_j = w.lr_j_a;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int os = __shfl_xor_sync(0xffffffffu, lr_best, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, lr_j, off);
+            if (os > lr_best || (os == lr_best && oj > lr_j)) { lr_best = os; lr_j = oj; }
+        }
+        if (!w.last_strip) {
+            if (lane == 0) { p.part_best[slot] = lr_best; p.part_j[slot] = lr_j; }
+            __syncwarp();
+            if (lane == 31) { __threadfence(); st_volatile(w.prog_out, M); }
+            continue;
+        }
+        // the last strip finishes last: fold the earlier strips' partials in (they lie to the left, so on ties
+        // the later strip wins, as `>=` does in the reference's left-to-right scan)
+        if (lane == 0) {
+            int best = -2147483647, bj = 0;
+            for (int s = 0; s < nstrips - 1; ++s) {
+                const int os = ld_cg(&p.part_best[pa.pad1 + s]), oj = ld_cg(&p.part_j[pa.pad1 + s]);
+                if (os >= best) { best = os; bj = oj; }
+            }
+            if (lr_best >= best) { best = lr_best; bj = lr_j; }
+            lr_best = best; lr_j = bj;
+        }
+        {
+            const int i_fin = nblk * STEPS - lane;
+            const int la = (Na - 1) / K - (nstrips - 1) * 32;
+            int best_a = (V::lo(w.best) >> 2) - (i_fin + Na) * p.gep;
+            best_a = __shfl_sync(0xffffffffu, best_a, la);
+            const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a, la);
+            if (lane == 0) {
+                if (lr_best > best_a) { p.score[task.pair_a] = lr_best; p.end_i[task.pair_a] = M; p.end_j[task.pair_a] = lr_j; }
+                else { p.score[task.pair_a] = best_a; p.end_i[task.pair_a] = bi_a; p.end_j[task.pair_a] = Na; }
             }
         }
     }

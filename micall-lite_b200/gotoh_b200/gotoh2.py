@@ -67,19 +67,23 @@ class Aligner:
         pairs = list(pairs)
         if not pairs:
             return []
-        s1 = [self.clean_sequence(a) for a, _ in pairs]
+        # identical first sequences (one reference against many reads) are packed once and shared through s1_idx
+        uniq, s1_idx = {}, np.zeros(len(pairs), np.int32)
+        for k, (a, _) in enumerate(pairs):
+            s1_idx[k] = uniq.setdefault(a, len(uniq))
+        s1 = [self.clean_sequence(a) for a in uniq]
         s2 = [self.clean_sequence(b) for _, b in pairs]
         b1, o1 = packing.pack(s1, "seq1")
         b2, o2 = packing.pack(s2, "seq2")
         n = len(pairs)
-        out_off = packing.out_offsets(o1, None, o2)
+        out_off = packing.out_offsets(o1, s1_idx, o2)
         out1 = np.zeros(int(out_off[-1]), np.uint8)
         out2 = np.zeros(int(out_off[-1]), np.uint8)
         out_len = np.zeros(n, np.int32)
         out_score = np.zeros(n, np.int32)
         mat = np.ascontiguousarray(self.matrix, dtype=np.int32)
         rc = self._libobj.lib.gotoh_b200_gotoh2_align_batch(
-            b1.ctypes.data, o1.ctypes.data, n, None, b2.ctypes.data, o2.ctypes.data, n,
+            b1.ctypes.data, o1.ctypes.data, len(s1), s1_idx.ctypes.data, b2.ctypes.data, o2.ctypes.data, n,
             int(self.gap_open_penalty), int(self.gap_extend_penalty), int(bool(self.is_global)),
             self.alphabet.encode("ascii"), mat.ctypes.data, out1.ctypes.data, out2.ctypes.data,
             out_off.ctypes.data, out_len.ctypes.data, out_score.ctypes.data, int(self.device))

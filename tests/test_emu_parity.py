@@ -87,7 +87,7 @@ def test_emu_many_reference_byte_classes(emu_aligner, oracle_port):
         assert g == oracle_port.align_it(ref, q, 10, 3, 1)
 
 
-@pytest.mark.parametrize("long_mode", ["cta", "warp"])
+@pytest.mark.parametrize("long_mode", ["flow", "cta", "warp"])
 def test_emu_long_pairs_cta_wavefront_and_warp_strips(emu_aligner, oracle_port, monkeypatch, long_mode):
     """K2: queries wider than 256 columns.  'cta' = one CTA per pair, 4 warps pipelined over adjacent
     strips (shared-memory rings + the cross-round column); 'warp' = one warp walks the strips."""

@@ -69,7 +69,7 @@ def test_gpu_c3_amino_vs_oracle(gpu_aligner, oracle_port, term, forced_path):
     _check_packed(gpu_aligner, oracle_port, 1, rb, ro, ridx, qb, qo, 40, 10, term)
 
 
-@pytest.mark.parametrize("long_mode", ["cta", "warp"])
+@pytest.mark.parametrize("long_mode", ["flow", "cta", "warp"])
 def test_gpu_c4_long_pairs_vs_oracle(gpu_aligner, oracle_port, monkeypatch, long_mode):
     """C4 shape: ~9.6 kb x ~9.6 kb, 38 strips of 256 columns per pair, IUPAC codes in the refs; both
     long-pair kernels (CTA wavefront / warp-serial strips)."""

@@ -84,7 +84,7 @@ def main():
     if a.c4:
         refs, ridx, qb, qo = workloads.c4_pairs_packed(a.c4)
         rb, ro = packing.pack(refs)
-        for mode in ("cta", "warp"):
+        for mode in ("flow", "cta", "warp"):
             os.environ["GOTOH_B200_LONG"] = mode
             run("C4 align_it(15,3,1) HCV genomes, long-pair kernel=%s" % mode, al, ora, gotoh_b200.NT, rb, ro, ridx, qb, qo,
                 15, 3, 1, max(1, a.steps - 1), min(a.verify, 6))

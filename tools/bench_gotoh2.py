@@ -74,6 +74,26 @@ def run(name, pairs, gop, gep, glob, model, steps, verify, cpu_seconds):
         e2e.append(dt)
         if best is None or s[1] < best[1]:
             best = s
+    # end to end through the C ABI: packed HOST arrays in, packed host arrays out (cleaning, packing, H2D, kernels, D2H)
+    from gotoh_b200 import packing
+    import numpy as np
+    b1, o1 = packing.pack([a for a, _ in pairs], "seq1")
+    b2, o2 = packing.pack([b for _, b in pairs], "seq2")
+    out_off = packing.out_offsets(o1, None, o2)
+    out1 = np.zeros(int(out_off[-1]), np.uint8); out2 = np.zeros(int(out_off[-1]), np.uint8)
+    out_len = np.zeros(len(pairs), np.int32); out_score = np.zeros(len(pairs), np.int32)
+    mat = np.ascontiguousarray(al.matrix, dtype=np.int32)
+    cabi = []
+    for it in range(steps + 1):
+        t0 = time.perf_counter()
+        rc = lib.gotoh_b200_gotoh2_align_batch(b1.ctypes.data, o1.ctypes.data, len(pairs), None, b2.ctypes.data, o2.ctypes.data,
+                                               len(pairs), gop, gep, int(glob), al.alphabet.encode("ascii"), mat.ctypes.data,
+                                               out1.ctypes.data, out2.ctypes.data, out_off.ctypes.data, out_len.ctypes.data,
+                                               out_score.ctypes.data, 0)
+        dt = time.perf_counter() - t0
+        al._libobj.check(rc)
+        if it:
+            cabi.append(dt)
     ora = Oracle2("port")
     idx = list(range(0, len(pairs), max(1, len(pairs) // verify)))
     bad = sum(out[k] != ora.align(pairs[k][0], pairs[k][1], gop, gep, glob, model) for k in idx)
@@ -82,7 +102,8 @@ def run(name, pairs, gop, gep, glob, model, steps, verify, cpu_seconds):
             "alignments_per_s": len(pairs) / (best[1] * 1e-3), "ms_kernels": best[1], "ms_forward": best[2],
             "ms_reverse": best[3], "ms_walk_emit": best[4], "gcups_forward": cells / (best[2] * 1e-3) / 1e9,
             "gcups_reverse": cells / (best[3] * 1e-3) / 1e9, "gpu_launches": best[5], "arena_bytes": best[6],
-            "chunks": best[7], "e2e_gcups_python_api": cells / min(e2e) / 1e9, "verified": len(idx), "mismatches": bad,
+            "chunks": best[7], "e2e_gcups_c_abi": cells / min(cabi) / 1e9, "e2e_s_c_abi": min(cabi),
+            "h2d_bytes": best[8], "d2h_bytes": best[9], "e2e_gcups_python_api": cells / min(e2e) / 1e9, "verified": len(idx), "mismatches": bad,
             "params": {"gop": gop, "gep": gep, "is_global": glob, "model": model}}
     if cpu_seconds > 0:
         line["cpu_baseline"] = cpu_baseline(pairs, gop, gep, glob, model, cpu_seconds)
