@@ -355,19 +355,86 @@ __device__ __forceinline__ unsigned compress_even(unsigned x) {
     return x;
 }
 
+// One warp sweeping one strip bottom-up.  All planes are K-bit masks (column k at bit K-1-k); pairs of planes travel
+// byte-packed in one register so that masks, shifts and the hand-over to the left lane act on several at once.
+template <int K, bool MULTI>
+struct Rev {
+    enum { KMASK = (1 << K) - 1 };
+    int lane, M;
+    bool last_strip, first_strip;
+    unsigned colmask, sent_last, sent_rows;
+    unsigned finA_dn, finC_dn, DE_dn;   // row below: final a, final c, forward d | e << 8
+    unsigned send;                      // top bits (my first column) of F, G, fin_b of the row just done and fin_c of the row below it
+    unsigned in_c_prev;                 // MULTI lane 31: fin_c of the right strip's first column, one row below
+    const uint8_t* ring;
+    uint8_t* rb_out;
+
+    template <bool SLOW>
+    __device__ __forceinline__ unsigned step(const int t, const unsigned wl, const unsigned wh) {
+        const int i = t - lane;
+        const bool valid = !SLOW || (i >= 1 && i <= M);
+        const unsigned m8 = valid ? colmask : 0u;
+        const unsigned sent = (SLOW && i == M) ? sent_last : sent_rows;
+        // forward bits of this row: 2-bit codes -> planes
+        const unsigned even = wl & 0x55555555u, odd = (wl >> 1) & 0x55555555u;
+        const unsigned eg = compress_even(even | odd);            // e | g << 16
+        const unsigned df = compress_even(odd ^ 0x55555555u);     // d | f << 16
+        const unsigned DE = __byte_perm(df, eg, 0x7740) & (m8 * 0x0101u);     // d | e << 8
+        const unsigned FG = __byte_perm(df, eg, 0x7762) & (m8 * 0x0101u);     // f | g << 8
+        const unsigned own = wh & (m8 * 0x010101u);                           // a | b << 8 | c << 16
+        // right neighbour column: lane+1 processed this row in its previous step
+        unsigned in = __shfl_down_sync(0xffffffffu, send, 1);
+        if (lane == 31) {
+            in = 0;
+            if (MULTI && !last_strip && valid) {
+                const int wdw = (t - 1) >> 5;
+                const unsigned x = ring[(wdw & 1) * 32 + (i - (32 * wdw - 30))];
+                in = (x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | (in_c_prev << 24);
+                in_c_prev = (x >> 3) & 1u;
+            }
+        }
+        const unsigned FGr = (((FG << 1) & 0xfefeu) | (in & 0x0101u)) & (KMASK * 0x0101u);   // f, g of the column to the right
+        const unsigned Fr = FGr & 0xffu, Gr = FGr >> 8;
+        const unsigned cin = (in >> 16) & 1u;
+        const unsigned C1 = ((((finC_dn << 1) | (in >> 24)) & KMASK) | sent) & m8;
+        const unsigned A1 = finA_dn, D_dn = DE_dn & 0xffu, E_dn = DE_dn >> 8;
+        const unsigned ownA = own & 0xffu, ownB = (own >> 8) & 0xffu, ownC = own >> 16;
+        const unsigned K0 = (A1 & E_dn) | C1;
+        const unsigned Gg = ownB & K0, Pp = (ownB & Gr) | Fr;
+        const unsigned x = Gg | Pp;
+        const unsigned cvec = (x + Gg + cin) ^ x ^ Gg;            // bit b: fin_b of the column right of bit b
+        const unsigned finB = (cvec >> 1) & m8;
+        const unsigned keepm = K0 | (cvec & Gr);                  // step 8 (_gotoh2.c:237-242)
+        const unsigned finA = (ownA & keepm) | (A1 & D_dn);       // step 10 (:251-270); A1 and own bits are already masked
+        const unsigned finC = ownC & keepm;
+        // hand-over to the left lane: top bits of f, g, fin_b of this row and of fin_c one row below
+        send = ((FG | (finB << 16) | (finC_dn << 24)) >> (K - 1)) & 0x01010101u;
+        if (MULTI && !first_strip && lane == 0 && valid) {
+            const unsigned y = ((FG | (finB << 16) | (finC << 24)) >> (K - 1)) & 0x01010101u;
+            rb_out[i] = (uint8_t)((y * 0x10204080u) >> 28);       // f | g << 1 | fin_b << 2 | fin_c << 3
+        }
+        finA_dn = finA; finC_dn = finC; DE_dn = DE;
+        return finA | (finB << 8) | (finC << 16);
+    }
+};
+
 template <int K, bool MULTI>
 __global__ void __launch_bounds__(128, 4) k2r(const Params p) {
-    enum { KMASK = (1 << K) - 1 };
+    typedef Rev<K, MULTI> R;
+    enum { KMASK = R::KMASK };
     __shared__ uint8_t s_ring[4][2][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned local = p.is_global ? 0u : 1u;
+    R r;
+    r.lane = lane;
+    r.ring = &s_ring[warp][0][0];
 
     for (;;) {
         unsigned tsk = 0;
         if (lane == 0) tsk = atomicAdd(p.counter_r, 1u);
         tsk = __shfl_sync(0xffffffffu, tsk, 0);
         if (tsk >= (unsigned)p.task_count) break;
-        const StripTask task = p.tasks[p.task_count - 1 - (int)tsk];      // (pair, strip) in strip-DEscending order
+        const StripTask task = p.tasks[p.task_count - 1 - (int)tsk];      // reversed claim order: a strip's right neighbour first
         const PairInfo pr = p.pairs[task.pair];
         const Extra ex = p.extra[task.pair];
         const int M = pr.M, N = pr.N, strip = task.strip, nstrips = ex.nstrips, nblk = pr.nblk;
@@ -377,31 +444,33 @@ __global__ void __launch_bounds__(128, 4) k2r(const Params p) {
         const int nreal = max(0, min(K, N - j0));
         const unsigned colmask = (unsigned)(KMASK & ~((1 << (K - nreal)) - 1));
         const unsigned bitN = (N > j0 && N <= j0 + K) ? (1u << (K - 1 - (N - j0 - 1))) : 0u;
-        const unsigned sent_last = local ? colmask : bitN;      // c of the sentinel row below row M (_gotoh2.c:118-133)
-        const unsigned sent_rows = local ? bitN : 0u;           // c of the sentinel column right of column N
-        const uint8_t* rb_in = p.rbnd + ex.bnd_off + (int64_t)strip * (M + 2);         // written by strip+1
-        uint8_t* rb_out = p.rbnd + ex.bnd_off + (int64_t)(strip - 1) * (M + 2);        // read by strip-1
+        r.M = M;
+        r.last_strip = last_strip;
+        r.first_strip = (strip == 0);
+        r.colmask = colmask;
+        r.sent_last = local ? colmask : bitN;       // c of the sentinel row below row M (_gotoh2.c:118-133)
+        r.sent_rows = local ? bitN : 0u;            // c of the sentinel column right of column N
+        r.finA_dn = 0; r.finC_dn = 0; r.DE_dn = 0; r.send = 0; r.in_c_prev = 0;
+        r.rb_out = p.rbnd + ex.bnd_off + (int64_t)(strip - 1) * (M + 2);                // read by strip-1
+        const uint8_t* rb_in = p.rbnd + ex.bnd_off + (int64_t)strip * (M + 2);          // written by strip+1
         int32_t* prog_in = p.prog_r + ex.slot0 + strip + 1;
         int32_t* prog_out = p.prog_r + ex.slot0 + strip;
         uint8_t* ring = &s_ring[warp][0][0];
 
-        unsigned finA_dn = 0, finC_dn = 0, D_dn = 0, E_dn = 0;   // row below (this lane's previous step)
-        unsigned send = 0;                                        // what lane-1 needs next step
-        unsigned finC_top_prev = 0;                               // fin_c of my first column, one row below the row in `send`
-        unsigned in_c_prev = 0;                                   // MULTI lane 31: fin_c of the right strip's first column, row below
         const uint4* slo = p.lo + pr.dir_off + (int64_t)strip * nblk * 32 + lane;
         uint4* shi = p.hi + pr.dir_off + (int64_t)strip * nblk * 32 + lane;
         __syncwarp();
         for (int tb = nblk - 1; tb >= 0; --tb) {
             const int t0 = tb * FSTEPS + 1, thi = t0 + FSTEPS - 1;
             if (MULTI && !last_strip && ((thi & 31) == 0 || tb == nblk - 1)) {
-                // lane 31 consumes rows thi-31 down to (thi&~31)+1-31... stage the 32 rows of this window:
-                // window index wdw = (thi-1)>>5 covers steps 32*wdw+1 .. 32*wdw+32, i.e. lane-31 rows 32*wdw-30 .. 32*wdw+1
+                // lane 31 consumes the right strip's first column: window wdw covers steps 32*wdw+1 .. 32*wdw+32,
+                // i.e. lane-31 rows 32*wdw-30 .. 32*wdw+1; all of them must have been published (counts down)
                 const int wdw = (thi - 1) >> 5;
                 const int lowrow = 32 * wdw - 30;
                 if (lane == 0) {
-                    const int need = max(lowrow, 1);          // rows >= need must be published (counts down)
+                    const int need = max(lowrow, 1);
                     while (ld_volatile(prog_in) > need) gotoh_pause();
+                    __threadfence();
                 }
                 __syncwarp();
                 const int row = lowrow + lane;
@@ -412,55 +481,17 @@ __global__ void __launch_bounds__(128, 4) k2r(const Params p) {
             }
             const uint4 l4 = slo[(int64_t)tb * 32];
             uint4 h4 = shi[(int64_t)tb * 32];
-#pragma unroll
-            for (int s = FSTEPS - 1; s >= 0; --s) {
-                const int t = t0 + s, i = t - lane;
-                const unsigned wl = s == 0 ? l4.x : s == 1 ? l4.y : s == 2 ? l4.z : l4.w;
-                const unsigned wh = s == 0 ? h4.x : s == 1 ? h4.y : s == 2 ? h4.z : h4.w;
-                const bool valid = (i >= 1 && i <= M);
-                const unsigned m8 = valid ? colmask : 0u;
-                // forward bits of this row
-                const unsigned even = wl & 0x55555555u, odd = (wl >> 1) & 0x55555555u;
-                const unsigned eg = compress_even(even | odd);            // e | g<<16
-                const unsigned df = compress_even(~odd & 0x55555555u);    // d | f<<16
-                const unsigned D = df & m8, E = eg & m8, F = (df >> 16) & m8, G = (eg >> 16) & m8;
-                const unsigned ownA = wh & m8, ownB = (wh >> 8) & m8, ownC = (wh >> 16) & m8;
-                // right neighbour column (lane+1 processed this row in its previous step)
-                unsigned in = __shfl_down_sync(0xffffffffu, send, 1);
-                if (lane == 31) {
-                    in = 0;
-                    if (MULTI && !last_strip && valid) {
-                        const int wdw = (t - 1) >> 5;
-                        const unsigned x = ring[(wdw & 1) * 32 + (i - (32 * wdw - 30))];
-                        in = (x & 7u) | (in_c_prev << 3);
-                        in_c_prev = (x >> 3) & 1u;
-                    }
-                }
-                const unsigned Fr = ((F << 1) | (in & 1u)) & KMASK;
-                const unsigned Gr = ((G << 1) | ((in >> 1) & 1u)) & KMASK;
-                const unsigned cin = (in >> 2) & 1u;
-                unsigned C1 = ((finC_dn << 1) | ((in >> 3) & 1u)) & KMASK;
-                C1 |= (i == M) ? sent_last : sent_rows;
-                C1 &= m8;
-                const unsigned A1 = finA_dn;
-                const unsigned K0 = (A1 & E_dn) | C1;
-                const unsigned Gg = ownB & K0, Pp = (ownB & Gr) | Fr;
-                const unsigned x = Gg | Pp, y = Gg;
-                const unsigned cvec = (x + y + cin) ^ x ^ y;             // bit b: fin_b of the column right of bit b
-                const unsigned B1 = cvec & KMASK;
-                const unsigned finB = (cvec >> 1) & m8;
-                const unsigned keepm = K0 | (B1 & Gr);                    // step 8 (_gotoh2.c:237-242)
-                const unsigned finA = ((ownA & keepm) | (A1 & D_dn)) & m8; // step 10 (:251-270)
-                const unsigned finC = ownC & keepm;
-                const unsigned nh = finA | (finB << 8) | (finC << 16);
-                if (s == 0) h4.x = nh; else if (s == 1) h4.y = nh; else if (s == 2) h4.z = nh; else h4.w = nh;
-                // hand-over to the left lane: F, G, fin_b of my first column at this row; fin_c of it one row below
-                const unsigned top = K - 1;
-                send = ((F >> top) & 1u) | (((G >> top) & 1u) << 1) | (((finB >> top) & 1u) << 2) | (finC_top_prev << 3);
-                if (MULTI && strip > 0 && lane == 0 && valid)
-                    rb_out[i] = (uint8_t)(((F >> top) & 1u) | (((G >> top) & 1u) << 1) | (((finB >> top) & 1u) << 2) | (((finC >> top) & 1u) << 3));
-                finC_top_prev = (finC >> top) & 1u;
-                finA_dn = finA; finC_dn = finC; D_dn = D; E_dn = E;
+            // FAST: every lane's rows of this block are inside 1 .. M-1
+            if (t0 >= 32 && thi < M) {
+                h4.w = r.template step<false>(t0 + 3, l4.w, h4.w);
+                h4.z = r.template step<false>(t0 + 2, l4.z, h4.z);
+                h4.y = r.template step<false>(t0 + 1, l4.y, h4.y);
+                h4.x = r.template step<false>(t0 + 0, l4.x, h4.x);
+            } else {
+                h4.w = r.template step<true>(t0 + 3, l4.w, h4.w);
+                h4.z = r.template step<true>(t0 + 2, l4.z, h4.z);
+                h4.y = r.template step<true>(t0 + 1, l4.y, h4.y);
+                h4.x = r.template step<true>(t0 + 0, l4.x, h4.x);
             }
             shi[(int64_t)tb * 32] = h4;
             if (MULTI && strip > 0 && ((t0 - 1) & (PUB - 1)) == 0 && t0 > 1 && t0 <= M) {

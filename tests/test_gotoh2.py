@@ -48,7 +48,10 @@ def _check_golden(make_aligner, max_cells):
 def _long_pairs(seed):
     rng = random.Random(seed)
     pairs = []
-    for l1, l2 in [(300, 600), (100, 1000), (700, 255), (64, 256), (513, 257), (40, 1300), (900, 300), (255, 512)]:
+    shapes = [(300, 600), (100, 1000), (700, 255), (64, 256), (513, 257), (40, 1300), (900, 300), (255, 512)]
+    # full-width single strips (8 columns per lane) and short, wide grids: the byte-packed planes of the reverse sweep
+    shapes += [(rng.randint(20, 90), rng.randint(200, 256)) for _ in range(24)] + [(rng.randint(30, 60), rng.randint(257, 700)) for _ in range(8)]
+    for l1, l2 in shapes:
         a = "".join(rng.choice("ACGT") for _ in range(l1))
         b = list((a * (l2 // l1 + 2))[:l2])
         for _ in range(l2 // 12):
