@@ -298,7 +298,10 @@ def run_ours(args, rank, world, local_rank):
                 "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_src": peaks_src,
                 "frac": (dir_bytes / (fwd_ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]) if fwd_ms_step else None,
                 "algorithmic_bytes_per_cell": 0.25},
-        "traffic": (sc or {}).get("ncu_dram_bytes_per_launch"),
+        # dram bytes of one forward launch: the per-cell figure of the committed ncu --set full capture
+        # (profiles/sass_counts.json: ncu_dram_bytes_per_cell, ncu_note) x the cells one launch of this run covers
+        "traffic": ((sc or {}).get("ncu_dram_bytes_per_cell") or 0) * cells / max(1, chunks) or None,
+        "algorithmic_bytes_per_launch": dir_bytes / max(1, chunks),
     }
 
     # ---- CPU baseline on the host cores (bounded sample) -----------------------------------------

@@ -30,7 +30,8 @@ struct G2Bufs {
     DevBuf<int2> fbnd;
     DevBuf<gotoh::g2f::Extra> extra;
     DevBuf<gotoh::g2f::StripTask> tasks;
-    ~G2Bufs() {
+    ~G2Bufs() { release_all(); }
+    void release_all() {
         raw1.release(); idx1.release(); raw2.release(); idx2.release(); o1.release(); o2.release(); rbnd.release();
         pairs.release(); dmat.release(); best.release(); si.release(); sj.release(); nops.release(); i0.release();
         j0.release(); lenp.release(); score.release(); olen.release(); oscore.release(); prog.release(); part.release();
@@ -38,6 +39,23 @@ struct G2Bufs {
         extra.release(); tasks.release();
     }
 };
+
+struct G2Cache {
+    std::mutex mu;
+    G2Bufs bufs;
+};
+std::mutex g2_cache_mu;
+G2Cache* g2_cache[64] = {nullptr};
+G2Cache* g2_cache_for(int dev) {
+    std::lock_guard<std::mutex> lk(g2_cache_mu);
+    if (!g2_cache[dev]) g2_cache[dev] = new (std::nothrow) G2Cache();
+    return g2_cache[dev];
+}
+void g2_release_cache() {
+    std::lock_guard<std::mutex> lk(g2_cache_mu);
+    for (int d = 0; d < 64; ++d)
+        if (g2_cache[d]) { std::lock_guard<std::mutex> lk2(g2_cache[d]->mu); g2_cache[d]->bufs.release_all(); }
+}
 
 struct G2Run {
     int64_t n = 0;
@@ -372,19 +390,21 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
         h_raw1.insert(h_raw1.end(), gotoh::REF_PAD, 0); h_idx1.insert(h_idx1.end(), gotoh::REF_PAD, 0);
     }
     std::vector<PairInfo> pairs((size_t)n_pairs);
-    int64_t ops_words = 0, max_rows = 0;
+    int64_t ops_words = 0, max_rows = 0, q_total = 0;
     long long cells = 0;
     for (int64_t k = 0; k < n_pairs; ++k) {
         PairInfo& pi = pairs[(size_t)k];
         memset(&pi, 0, sizeof(pi));
         const int64_t r = s1_idx ? local[(size_t)s1_idx[k]] : k;
         const int64_t u1 = used[(size_t)r];
+        const int64_t len2 = s2_off[k + 1] - s2_off[k];
+        if (len2 <= 0) return fail(GOTOH_B200_EEMPTY, "seq2 %lld is empty (gotoh2.py:84-85 asserts non-empty)", (long long)k);
+        if (len2 >= (1 << 24)) return fail(GOTOH_B200_ERANGE, "seq2 %lld too long", (long long)k);
         pi.ref_pos = pos1[(size_t)r];
-        pi.qry_pos = (int64_t)h_raw2.size();
-        const int rc = add_seq(s2_bytes + s2_off[k], s2_off[k + 1] - s2_off[k], map2, h_raw2, h_idx2, "seq2", (long long)k);
-        if (rc) return rc;
+        pi.qry_pos = q_total;
+        q_total += len2;
         pi.M = (int32_t)(s1_off[u1 + 1] - s1_off[u1]);
-        pi.N = (int32_t)(s2_off[k + 1] - s2_off[k]);
+        pi.N = (int32_t)len2;
         pi.nblk = pi.M + 1 + 31;                     // T: steps of the wavefront over the (l1+1)-row grid
         pi.K = G2K;
         pi.orig = (int32_t)k;
@@ -403,6 +423,30 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
         if ((long long)(pi.M + pi.N + 2) * (std::abs(gop) + std::abs(gep) + 64) > (1LL << 27))
             return fail(GOTOH_B200_ERANGE, "pair %lld: penalties x lengths exceed the int32 cost range", (long long)k);
     }
+    // second sequences: clean + index in parallel into their final positions
+    h_raw2.resize((size_t)q_total);
+    h_idx2.resize((size_t)q_total);
+    {
+        const int nthreads = host_threads(q_total);
+        std::vector<int64_t> bad_pair((size_t)nthreads, -1);
+        std::vector<int> bad_byte((size_t)nthreads, 0);
+        parallel_for(n_pairs, nthreads, [&](int64_t lo_k, int64_t hi_k, int tid) {
+            for (int64_t k = lo_k; k < hi_k; ++k) {
+                const uint8_t* src = s2_bytes + s2_off[k];
+                const int64_t len = s2_off[k + 1] - s2_off[k], at = pairs[(size_t)k].qry_pos;
+                for (int64_t x = 0; x < len; ++x) {
+                    const int c = map2.cls[src[x]];
+                    if (c < 0) { if (bad_pair[(size_t)tid] < 0) { bad_pair[(size_t)tid] = k; bad_byte[(size_t)tid] = src[x]; } return; }
+                    h_raw2[(size_t)(at + x)] = map2.clean[src[x]];
+                    h_idx2[(size_t)(at + x)] = (uint8_t)c;
+                }
+            }
+        });
+        for (int t = 0; t < nthreads; ++t)
+            if (bad_pair[(size_t)t] >= 0)
+                return fail(GOTOH_B200_EDOMAIN, "seq2 %lld: byte 0x%02x is not in the alphabet and the alphabet has no '?'",
+                            (long long)bad_pair[(size_t)t], bad_byte[(size_t)t]);
+    }
     for (int x = 0; x < l * l; ++x)
         if (std::abs(matrix[x]) > 1000000) return fail(GOTOH_B200_ERANGE, "substitution score out of range");
 
@@ -410,7 +454,12 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    G2Bufs b;
+    // grow-only device buffers, cached per device between calls (gotoh_b200_release_cache frees them): a call on a
+    // few hundred pairs must not pay for cudaMalloc/cudaFree of the tie-bit arena
+    G2Cache* cache = g2_cache_for(device);
+    if (!cache) return fail(GOTOH_B200_ENOMEM, "out of host memory");
+    std::lock_guard<std::mutex> cache_lock(cache->mu);
+    G2Bufs& b = cache->bufs;
     const size_t n = (size_t)n_pairs;
     const int64_t out_bytes = score_only ? 0 : out_off[n_pairs] - out_off[0];
     CU(b.raw1.ensure(h_raw1.size())); CU(b.idx1.ensure(h_idx1.size()));

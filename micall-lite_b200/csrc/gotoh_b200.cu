@@ -1093,7 +1093,10 @@ extern "C" int64_t gotoh_b200_plan_stat(const gotoh_b200_plan* pl, int32_t what)
     return -1;
 }
 
+namespace { void g2_release_cache(); }   // gotoh2_host.cuh
+
 extern "C" void gotoh_b200_release_cache(void) {
+    g2_release_cache();
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     for (int d = 0; d < 64; ++d)
         if (g_ctx[d]) {

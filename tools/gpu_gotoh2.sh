@@ -4,13 +4,13 @@
 set -u
 mkdir -p gpurun_out
 timeout ${BENCH_TIMEOUT:-900} python tools/bench_gotoh2.py ${BENCH_ARGS:-} > gpurun_out/gotoh2_bench.jsonl 2> gpurun_out/gotoh2_bench.err; echo "bench_gotoh2 rc=$?"
-cat gotoh2_bench.jsonl 2>/dev/null; tail -c 6000 gpurun_out/gotoh2_bench.jsonl; tail -5 gpurun_out/gotoh2_bench.err
+tail -c 6000 gpurun_out/gotoh2_bench.jsonl; tail -5 gpurun_out/gotoh2_bench.err
 if [ "${NCU:-1}" = "1" ]; then
 CMD="python tools/bench_gotoh2.py --remap 0 --aa 0 --reads 4000 --steps 1 --cpu-seconds 0"
 $CMD > gpurun_out/gotoh2_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/gotoh2_launches.csv $CMD > gpurun_out/gotoh2_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"; tail -2 gpurun_out/gotoh2_plain.log
 $CMD > gpurun_out/gotoh2_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'k2_forward|k2_reverse|k2f|k2r' -s 2 -c 2 -f -o gpurun_out/prof_gotoh2 $CMD > gpurun_out/gotoh2_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'^k2f$|^k2r$' -s 2 -c 2 -f -o gpurun_out/prof_gotoh2 $CMD > gpurun_out/gotoh2_ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -3 gpurun_out/gotoh2_ncu_full.log
 fi

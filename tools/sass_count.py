@@ -120,7 +120,7 @@ def main():
     if os.path.exists(prev):
         try:
             old = json.load(open(prev))
-            for key in ("ncu_dram_bytes_per_launch", "ncu_note"):
+            for key in ("ncu_dram_bytes_per_launch", "ncu_dram_bytes_per_cell", "ncu_note"):
                 if key in old:
                     doc[key] = old[key]
         except Exception:
