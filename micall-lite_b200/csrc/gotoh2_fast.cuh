@@ -419,7 +419,7 @@ struct Rev {
 };
 
 template <int K, bool MULTI>
-__global__ void __launch_bounds__(128, 4) k2r(const Params p) {
+__global__ void __launch_bounds__(128, 8) k2r(const Params p) {
     typedef Rev<K, MULTI> R;
     enum { KMASK = R::KMASK };
     __shared__ uint8_t s_ring[4][2][32];
@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(128, 4) k2r(const Params p) {
         const uint4* slo = p.lo + pr.dir_off + (int64_t)strip * nblk * 32 + lane;
         uint4* shi = p.hi + pr.dir_off + (int64_t)strip * nblk * 32 + lane;
         __syncwarp();
+        uint4 nl4 = slo[(int64_t)(nblk - 1) * 32], nh4 = shi[(int64_t)(nblk - 1) * 32];
         for (int tb = nblk - 1; tb >= 0; --tb) {
             const int t0 = tb * FSTEPS + 1, thi = t0 + FSTEPS - 1;
             if (MULTI && !last_strip && ((thi & 31) == 0 || tb == nblk - 1)) {
@@ -479,8 +480,9 @@ __global__ void __launch_bounds__(128, 4) k2r(const Params p) {
                 ring[(wdw & 1) * 32 + lane] = b;
                 __syncwarp();
             }
-            const uint4 l4 = slo[(int64_t)tb * 32];
-            uint4 h4 = shi[(int64_t)tb * 32];
+            const uint4 l4 = nl4;
+            uint4 h4 = nh4;
+            if (tb > 0) { nl4 = slo[(int64_t)(tb - 1) * 32]; nh4 = shi[(int64_t)(tb - 1) * 32]; }   // prefetch the next block
             // FAST: every lane's rows of this block are inside 1 .. M-1
             if (t0 >= 32 && thi < M) {
                 h4.w = r.template step<false>(t0 + 3, l4.w, h4.w);

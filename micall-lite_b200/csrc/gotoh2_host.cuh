@@ -170,7 +170,7 @@ int g2_launch_fwd(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
 template <int K, bool MULTI>
 int g2_launch_rev(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
     using namespace gotoh::g2f;
-    const int grid = std::max(1, std::min((ntasks + 3) / 4, run.sm_count * 4));
+    const int grid = std::max(1, std::min((ntasks + 3) / 4, run.sm_count * 8));
     GOTOH_LAUNCH((k2r<K, MULTI>), dim3(grid), dim3(128), 0, (cudaStream_t)0, p);
     CU(cudaGetLastError());
     return 0;

@@ -138,3 +138,22 @@ def test_gpu_gotoh2_shapes_vs_oracle(gpu_aligner, oracle2_port):
     for (a, b), o in zip(rp, al.align_batch(rp)):
         assert o == oracle2_port.align(a, b, 10, 3, False, "HYPHY_NUC")
     del rng
+
+
+@pytest.mark.gpu
+def test_gpu_gotoh2_large_batch_properties(gpu_aligner, oracle2_port):
+    """50,000 reads against the HXB2 pol seed through Aligner.align_batch (local mode, the aln2counts/remap style of
+    call): on every pair the two aligned strings have equal length, no column pairs two gaps and removing the gaps
+    gives back the cleaned inputs; 250 pairs are compared with the oracle."""
+    from gotoh_b200 import workloads
+    from gotoh_b200.gotoh2 import Aligner
+    ref, reads = workloads.c2_reads(50000, seed=21)
+    al = Aligner(10, 3, False, "HYPHY_NUC", library=gpu_aligner._libobj)
+    out = al.align_batch([(ref, r) for r in reads])
+    cref = al.clean_sequence(ref)
+    for k, (a, b, score) in enumerate(out):
+        assert len(a) == len(b)
+        assert a.replace("-", "") == cref and b.replace("-", "") == al.clean_sequence(reads[k])
+        assert not any(x == "-" and y == "-" for x, y in zip(a[:40], b[:40]))
+        if k % 200 == 0:
+            assert (a, b, score) == oracle2_port.align(ref, reads[k], 10, 3, False, "HYPHY_NUC")

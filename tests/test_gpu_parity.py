@@ -198,3 +198,58 @@ def test_gpu_multi_device_sharding_matches_single(gpu_aligner):
 def test_gpu_int_peak_microbenchmarks_run(gpu_aligner):
     v = gpu_aligner.int_peak(2)
     assert v > 100.0   # G thread-instructions/s; a B200 does thousands
+
+
+def _check_chunk_properties(out_a, out_b, out_off, out_len, M, N, c0, c1):
+    """Pairs c0..c1: gaps removed, the aligned strings hold M reference and N query characters; no column pairs two
+    gaps; the bytes between out_len and the stride are zero.  Vectorised over one chunk of the packed outputs."""
+    base = int(out_off[c0])
+    a = out_a[base:int(out_off[c1])]
+    b = out_b[base:int(out_off[c1])]
+    rel = (out_off[c0:c1 + 1] - base).astype(np.int64)
+    ln = out_len[c0:c1].astype(np.int64)
+    inside = np.zeros(len(a) + 1, np.int32)
+    np.add.at(inside, rel[:-1], 1)
+    np.add.at(inside, rel[:-1] + ln, -1)
+    inside = np.cumsum(inside[:-1]) > 0                       # positions below out_len of their pair
+    assert not a[~inside].any() and not b[~inside].any(), "stride tail is not zero"
+    assert not ((a == ord("-")) & (b == ord("-")) & inside).any(), "a column pairs two gaps"
+    ca = np.add.reduceat(((a != ord("-")) & inside).astype(np.int32), rel[:-1])
+    cb = np.add.reduceat(((b != ord("-")) & inside).astype(np.int32), rel[:-1])
+    assert (ca == M).all(), "aligned reference does not hold the reference's characters"
+    assert (cb == N[c0:c1]).all(), "aligned query does not hold the query's characters"
+
+
+def test_gpu_full_size_c2_properties(gpu_aligner, oracle_port):
+    """BASELINE.json configs[1] at FULL size (1,000,000 reads vs HXB2 pol) through the one-shot C-ABI call, checked by
+    size-independent properties on every pair - removing the gaps from the two aligned strings gives back M reference
+    and N query characters, no column pairs two gaps, lengths within M+N, stride tails are zero - plus a batch-order
+    check (a reversed batch gives the reversed outputs) and 500 pairs against the oracle."""
+    from gotoh_b200 import packing, workloads
+    n = 1000000
+    ref, qb, qo = workloads.c2_reads_packed(n, seed=77)
+    rb, ro = packing.pack([ref])
+    ridx = np.zeros(n, np.int32)
+    out_off = packing.out_offsets(ro, ridx, qo)
+    out_a, out_b, _, out_len, score = gpu_aligner.align_packed(rb, ro, ridx, qb, qo, 10, 3, 1, 0, out_off=out_off)
+    M, N = len(ref), np.diff(qo)
+    assert (out_len >= np.maximum(M, N)).all() and (out_len <= M + N).all()
+    for c0 in range(0, n, 50000):
+        _check_chunk_properties(out_a, out_b, out_off, out_len, M, N, c0, min(n, c0 + 50000))
+    for k in range(0, n, n // 500):
+        q = qb[qo[k]:qo[k + 1]].tobytes().decode()
+        s = int(out_off[k])
+        exp = oracle_port.align_it(ref, q, 10, 3, 1)
+        assert (out_a[s:s + out_len[k]].tobytes().decode(), out_b[s:s + out_len[k]].tobytes().decode(), int(score[k])) == exp
+    # batch-order independence on the first 100,000 pairs: reversed order in, reversed results out
+    m = 100000
+    rq_off = np.zeros(m + 1, np.int64)
+    np.cumsum(N[:m][::-1], out=rq_off[1:])
+    rq = np.concatenate([qb[qo[k]:qo[k + 1]] for k in range(m - 1, -1, -1)])
+    r_off = packing.out_offsets(ro, ridx[:m], rq_off)
+    g2 = gpu_aligner.align_packed(rb, ro, ridx[:m], rq, rq_off, 10, 3, 1, 0, out_off=r_off)
+    assert (g2[4][::-1] == score[:m]).all() and (g2[3][::-1] == out_len[:m]).all()
+    for k in range(0, m, m // 1000):
+        s1, s2 = int(out_off[k]), int(r_off[m - 1 - k])
+        assert (out_b[s1:s1 + out_len[k]] == g2[1][s2:s2 + out_len[k]]).all()
+        assert (out_a[s1:s1 + out_len[k]] == g2[0][s2:s2 + out_len[k]]).all()
