@@ -238,9 +238,9 @@ def test_gpu_full_size_c2_properties(gpu_aligner, oracle_port):
         _check_chunk_properties(out_a, out_b, out_off, out_len, M, N, c0, min(n, c0 + 50000))
     for k in range(0, n, n // 500):
         q = qb[qo[k]:qo[k + 1]].tobytes().decode()
-        s = int(out_off[k])
+        s, ln = int(out_off[k]), int(out_len[k])
         exp = oracle_port.align_it(ref, q, 10, 3, 1)
-        assert (out_a[s:s + out_len[k]].tobytes().decode(), out_b[s:s + out_len[k]].tobytes().decode(), int(score[k])) == exp
+        assert (out_a[s:s + ln].tobytes().decode(), out_b[s:s + ln].tobytes().decode(), int(score[k])) == exp
     # batch-order independence on the first 100,000 pairs: reversed order in, reversed results out
     m = 100000
     rq_off = np.zeros(m + 1, np.int64)
@@ -250,6 +250,6 @@ def test_gpu_full_size_c2_properties(gpu_aligner, oracle_port):
     g2 = gpu_aligner.align_packed(rb, ro, ridx[:m], rq, rq_off, 10, 3, 1, 0, out_off=r_off)
     assert (g2[4][::-1] == score[:m]).all() and (g2[3][::-1] == out_len[:m]).all()
     for k in range(0, m, m // 1000):
-        s1, s2 = int(out_off[k]), int(r_off[m - 1 - k])
-        assert (out_b[s1:s1 + out_len[k]] == g2[1][s2:s2 + out_len[k]]).all()
-        assert (out_a[s1:s1 + out_len[k]] == g2[0][s2:s2 + out_len[k]]).all()
+        s1, s2, ln = int(out_off[k]), int(r_off[m - 1 - k]), int(out_len[k])
+        assert (out_b[s1:s1 + ln] == g2[1][s2:s2 + ln]).all()
+        assert (out_a[s1:s1 + ln] == g2[0][s2:s2 + ln]).all()
