@@ -202,6 +202,7 @@ struct gotoh_b200_plan {
     int64_t pair_base = 0;                 // first caller pair index
     int64_t bnd_stride = 0;
     int flow_slots = 0;                    // > 0: the strip-dataflow kernel can run (boundary columns allocated)
+    int task_limit = 0;                    // one-shot pipeline: tasks per warp before a forward CTA retires (0 = persistent)
     int64_t n_stasks = 0;
     int64_t arena_budget_bytes = 0;        // 0: 80 % of free memory
     // stats
@@ -277,10 +278,13 @@ inline double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 thread_local double g_trace_phase[8];
 
 int host_threads(int64_t bytes) {
+    // one thread per MB of input, at most 16 (or GOTOH_B200_HOST_THREADS): spawning 16 threads for a 4 MB slab costs
+    // more CPU than the packing itself, and under torchrun the ranks share the host's cores
     if (bytes < (1 << 20)) return 1;
     const char* e = getenv("GOTOH_B200_HOST_THREADS");
     int hw = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-    return std::max(1, std::min(hw, 16));
+    hw = std::max(1, std::min(hw, 16));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(hw, bytes >> 20));
 }
 
 template <class V, int K, bool MULTI>
@@ -296,6 +300,9 @@ int launch_forward_k(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
     // persistent grid: enough CTAs to fill every SM, tasks are pulled from a counter
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(GOTOH_MIN_CTAS, (200 * 1024) / std::max<size_t>(smem, 1)));
     int grid = std::min((ntasks + warps - 1) / warps, ws->sm_count * ctas_per_sm);
+    // task_limit > 0 (one-shot pipeline): CTAs retire after task_limit tasks per warp, so the short traceback / emit
+    // kernels of the previous slab (other streams) get SM slots while this launch is still running
+    if (fp.task_limit > 0 && !MULTI) grid = (ntasks + warps * fp.task_limit - 1) / (warps * fp.task_limit);
     if (MULTI) grid = std::min<long long>(grid, (long long)ws->d_bnd.cap / (2 * pl->bnd_stride * warps));
     grid = std::max(grid, 1);
     GOTOH_LAUNCH((k_forward<V, K, MULTI>), dim3(grid), dim3(warps * 32), smem, ws->stream, fp);
@@ -811,6 +818,7 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
             fp.bnd = L.multi_strip ? ws->d_bnd.p : nullptr; fp.bnd_stride = pl->bnd_stride;
             fp.score = ws->d_score.p; fp.end_i = ws->d_end_i.p; fp.end_j = ws->d_end_j.p;
             fp.work_counter = ws->d_counter.p + launch_no++;
+            fp.task_limit = (!timed && !L.multi_strip) ? pl->task_limit : 0;
             // multi-strip tasks only exist with K = 8 (pick_K), and only on the int32 path
             int rc;
             if (L.x2) rc = launch_forward<Vec16, false>(pl, fp, L.K, L.task_count);
@@ -945,6 +953,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
         plans[w].ws = &ctx->ws[w];
         plans[w].gip = gip; plans[w].gep = gep; plans[w].term = term ? 1 : 0; plans[w].matrix = matrix_id;
         plans[w].arena_budget_bytes = slab_budget;
+        plans[w].task_limit = getenv("GOTOH_B200_TASK_LIMIT") ? atoi(getenv("GOTOH_B200_TASK_LIMIT")) : 0;   // measured: no gain over persistent warps
     }
     // slab = as many consecutive pairs as fit the arena estimate ((M+40)*64 B per strip per pair).  (Ramping the slab
     // size up and down to shorten the pipeline's fill and drain was tried and measured slower on B200 than equal slabs.)

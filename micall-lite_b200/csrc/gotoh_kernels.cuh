@@ -91,6 +91,7 @@ struct FwdParams {
     int32_t* end_j;
     uint32_t* work_counter;     // dynamic task scheduler
     // strip dataflow (k_forward_flow): tasks are (pair_a = pair, pair_b = strip); slot = pairs[pair].pad1 + strip
+    int32_t task_limit;         // 0: persistent warps drain the queue; n > 0: a warp retires after n tasks (see plan_run)
     int32_t* prog;              // rows published per slot
     int32_t* part_best;         // last-row partial maximum per slot
     int32_t* part_j;
@@ -493,8 +494,9 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
     w.inj_s = lane == 0 ? V::raw(w.c_sl0) : 0u;
     w.inj_q = lane == 0 ? V::raw(w.c_q0) : 0u;
 
-    for (;;) {
+    for (int done = 0;; ++done) {
         // ---- dynamic task fetch (one atomic per warp) ---------------------------------------
+        if (p.task_limit > 0 && done >= p.task_limit) break;
         unsigned tsk = 0;
         if (lane == 0) tsk = atomicAdd(p.work_counter, 1u);
         tsk = __shfl_sync(0xffffffffu, tsk, 0);
