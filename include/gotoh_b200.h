@@ -163,9 +163,10 @@ int32_t gotoh_b200_edit_distance_batch(const uint8_t* a_bytes, const int64_t* a_
                                        int32_t* out_dist, int32_t device);
 
 /* Statistics of the calling thread's last gotoh_b200_gotoh2_align_batch or gotoh_b200_edit_distance_batch (benchmarks, tests): fills up to
- * n <= 10 doubles and returns how many: 0 grid cells sum (l1+1)(l2+1), 1 device ms of all kernels (CUDA
+ * n <= 11 doubles and returns how many: 0 grid cells sum (l1+1)(l2+1), 1 device ms of all kernels (CUDA
  * events), 2 forward ms, 3 reverse-sweep ms, 4 walk+emit ms, 5 kernel launches, 6 tie-bit arena bytes,
- * 7 arena chunks, 8 bytes copied H2D, 9 bytes copied D2H. */
+ * 7 arena chunks, 8 bytes copied H2D, 9 bytes copied D2H, 10 forward warp tasks that ran in int16x2 (two pairs sharing seq1
+ * per warp; 0 when the 16-bit range proof failed or GOTOH_B200_GOTOH2=x1 pinned the int32 forward kernel). */
 int32_t gotoh_b200_gotoh2_last_stats(double* out, int32_t n);
 
 /* Integer-issue microbenchmark used for the roofline denominator ("peak

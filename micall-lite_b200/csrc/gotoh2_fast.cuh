@@ -53,6 +53,7 @@ struct Params {
     int32_t l, v, u, is_global; // v = gap open, u = gap extend (_gotoh2.c:31-32)
     uint32_t two, four;         // == 2, 4 at run time; opaque so acc*two+x stays an IMAD (FMA pipe)
     uint32_t neg1;              // == 0xffffffff at run time: c - r as r*neg1 + c on the FMA pipe
+    int32_t inf16, shift16;     // k2f_x2: +infinity (already shifted) and the frame shift S of the 16-bit frame (host: g2_fits_int16)
     uint4* lo;                  // plane 0: code_DE | code_FG << 16, one word per lane-step
     uint4* hi;                  // plane 1: a | b << 8 | c << 16 (k2f: forward bits, k2r: final bits)
     int2* bnd;                  // forward strip boundaries (R~, q~) per row
@@ -340,6 +341,267 @@ __global__ void __launch_bounds__(128, 4) k2f(const Params p) {
             p.best[task.pair] = best;
             p.start_i[task.pair] = bi;
             p.start_j[task.pair] = bj;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// forward, int16x2: two pairs that share seq1 in the halves of one register (single strip only)
+// -------------------------------------------------------------------------------------------------------
+// In the frame X~ = X - (i+j)*u every value of a pair lies in [-(dmax*min(l1,l2) + (l1+l2)*u), 3v], so short second
+// sequences fit 16 bits whatever the length of the first (the host proves it per pair, g2_fits_int16).  The cell is
+// the int32 one with VIADDMNMX.S16x2 / VIMNMX3.S16x2 (7 + 1 ALU-pipe instructions per cell COUPLE).  Everything else
+// is moved to the FMA pipe by a second shift of the frame, X' = X~ - S with S = p.shift16 > 4v - dmin:
+//   * every R' and every diagonal candidate dg' is then strictly NEGATIVE and every negated value (1-v) - R', -R' is
+//     strictly POSITIVE in both halves;
+//   * a packed word whose low half is negative equals the "linear" word lo + 65536*hi plus 65536, a packed word whose
+//     low half is non-negative equals it exactly, and linear words add and negate component-wise in plain 32-bit
+//     arithmetic.  Hence   dg' = rdiag'*1 + lin(e)          (profile entries are stored linear, not packed)
+//                          nr  = R'*(-1) + lin(1-v) + 65536  ((1-v) - R' per half)
+//                          nn  = R'*(-1) + 65536             (-R' per half)
+//     are single IMADs (multipliers opaque run-time values so ptxas keeps them on the FMA pipe) instead of the
+//     LOP3 + 2 VIADD.16x2 a per-half subtraction costs.
+// S cancels in every recurrence and tie code (they are differences); it enters row 0 / column 0 and is added back when
+// the start-cell candidates are unframed.  Each pair still gets its own two planes in the int32 layout, so k2r and the
+// traceback kernels are unchanged.
+__device__ __forceinline__ unsigned pk2(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+__device__ __forceinline__ unsigned lin2(int lo, int hi) { return (unsigned)lo + ((unsigned)hi << 16); }
+__device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); }
+
+template <int K>
+struct FwdX2 {
+    enum { K4 = (K + 3) / 4, KMASK = (1 << K) - 1 };
+    int lane, M, Na, Nb, j0, u, v, inf16, S;
+    unsigned one, two, four, neg1, keep;
+    unsigned v2, negu2, c_nr, c_nn, injq, c0run, c0step;
+    const uint4* prof_lane;
+    const uint8_t* cls;
+    unsigned vq[K];
+    unsigned R[K], P[K], nRu[K];
+    unsigned sendR, sendQ, Rd_in;
+    int next_cls;
+    unsigned bf;
+    int best_i_a, best_i_b;
+    int row_min_a, row_j_a, r_ll_a, row_min_b, row_j_b, r_ll_b;
+    uint4 wlo_a, whi_a, wlo_b, whi_b;
+
+    // row 0 in the shifted frame (_gotoh2.c:96-116): R'(0,j) = v - S (global) or -j*u - S (local), p(0,j) = +inf
+    __device__ __forceinline__ int row0(int j, int is_global) const { return (j == 0 ? 0 : (is_global ? v : -j * u)) - S; }
+    __device__ __forceinline__ void row0_init(int is_global) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int ra = row0(min(j0 + k + 1, Na), is_global), rb = row0(min(j0 + k + 1, Nb), is_global);
+            R[k] = pk2(ra, rb);
+            P[k] = pk2(inf16, inf16);
+            nRu[k] = pk2(1 - v - ra, 1 - v - rb);
+        }
+        Rd_in = pk2(row0(min(j0, Na), is_global), row0(min(j0, Nb), is_global));
+        bf = pk2(row0(Na, is_global), row0(Nb, is_global));
+        best_i_a = best_i_b = 0;
+    }
+
+    template <bool SLOW>
+    __device__ __forceinline__ void step(const int t, const int s, const int is_global) {
+        const int i = t - lane;
+        const int my_cls = next_cls;
+        next_cls = cls[i];
+        unsigned Rl = __shfl_up_sync(0xffffffffu, sendR, 1);
+        unsigned Ql = __shfl_up_sync(0xffffffffu, sendQ, 1);
+        unsigned rdiag = Rd_in;
+        c0run = __vadd2(c0run, c0step);                 // column 0 (_gotoh2.c:101-116), both halves alike
+        Rl = Rl * keep + c0run;
+        Ql = Ql * keep + injq;
+        Rd_in = Rl;
+
+        const uint4* prow = prof_lane + my_cls * (K4 * 32);
+        unsigned Rleft = Rl, nRleft = Rl * neg1 + c_nr, q = Ql;
+        unsigned accDE = 0, accFG = 0, accA = 0, accB = 0, accC = 0;
+#pragma unroll
+        for (int kq = 0; kq < K4; ++kq) {
+            const uint4 e4 = prow[kq * 32];
+            const unsigned ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = kq * 4 + kk;
+                if (k < K) {
+                    const unsigned cFG = __viaddmin_s16x2_relu(q, nRleft, 0x00020002u);      // _gotoh2.c:167-173
+                    const unsigned cDE = __viaddmin_s16x2_relu(P[k], nRu[k], 0x00020002u);   // _gotoh2.c:157-163
+                    accFG = accFG * four + cFG;
+                    accDE = accDE * four + cDE;
+                    q = __viaddmin_s16x2(Rleft, vq[k], q);                                    // _gotoh2.c:166
+                    const unsigned p = __viaddmin_s16x2(R[k], v2, P[k]);                      // _gotoh2.c:156
+                    const unsigned dg = rdiag * one + ev[kk];                                 // _gotoh2.c:185 (linear add)
+                    const unsigned r = __vimin3_s16x2(dg, p, q);                              // _gotoh2.c:186-187
+                    const unsigned nn = r * neg1 + c_nn;                                      // -R' per half
+                    const unsigned nr = r * neg1 + c_nr;                                      // (1-v) - R' per half
+                    accA = accA * two + __viaddmin_s16x2(p, nn, 0x00010001u);                 // [R != p]    (:190-192)
+                    accB = accB * two + __viaddmin_s16x2(q, nn, 0x00010001u);                 // [R != q]    (:193-195)
+                    accC = accC * two + __viaddmin_s16x2(dg, nn, 0x00010001u);                // [R != diag] (:196-198)
+                    rdiag = R[k];
+                    R[k] = r; P[k] = p; nRu[k] = nr;
+                    Rleft = r; nRleft = nr;
+                }
+            }
+        }
+        sendR = R[K - 1];
+        sendQ = q;
+        {
+            // per pair: lo = code_DE | code_FG << 16, hi = a | b << 8 | c << 16 (bits are "equal" = NOT of the accumulated)
+            const unsigned nA = accA ^ (KMASK * 0x00010001u), nB = accB ^ (KMASK * 0x00010001u), nC = accC ^ (KMASK * 0x00010001u);
+            const unsigned la = __byte_perm(accDE, accFG, 0x5410), lb = __byte_perm(accDE, accFG, 0x7632);
+            const unsigned ha = __byte_perm(__byte_perm(nA, nB, 0x4440), nC, 0x7410);
+            const unsigned hb = __byte_perm(__byte_perm(nA, nB, 0x6662), nC, 0x7610);
+            if (s == 0) { wlo_a.x = la; whi_a.x = ha; wlo_b.x = lb; whi_b.x = hb; }
+            else if (s == 1) { wlo_a.y = la; whi_a.y = ha; wlo_b.y = lb; whi_b.y = hb; }
+            else if (s == 2) { wlo_a.z = la; whi_a.z = ha; wlo_b.z = lb; whi_b.z = hb; }
+            else { wlo_a.w = la; whi_a.w = ha; wlo_b.w = lb; whi_b.w = hb; }
+        }
+        // last column: first strict minimum scanning top-down (_gotoh2.c:330-339), per half
+        bf = __vadd2(bf, negu2);
+        {
+            bool keep_hi, keep_lo;                        // bf <= R: no new minimum
+            const unsigned nb = __vibmin_s16x2(bf, R[K - 1], &keep_hi, &keep_lo);
+            if (!SLOW || (i >= 1 && i <= M)) {
+                bf = nb;
+                if (!keep_lo) best_i_a = i;
+                if (!keep_hi) best_i_b = i;
+            }
+        }
+        if (SLOW) {
+            if (i == 0) row0_init(is_global);
+            if (i == M) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int j = j0 + k + 1;
+                    const int va = lo16(R[k]) + (M + j) * u + S, vb = hi16(R[k]) + (M + j) * u + S;
+                    if (j <= Na && va < row_min_a) { row_min_a = va; row_j_a = j; }
+                    if (j <= Nb && vb < row_min_b) { row_min_b = vb; row_j_b = j; }
+                }
+                r_ll_a = lo16(R[K - 1]) + (M + Na) * u + S;
+                r_ll_b = hi16(R[K - 1]) + (M + Nb) * u + S;
+            }
+        }
+    }
+};
+
+// tasks: (pair = first pair, strip = second pair or -1)
+template <int K>
+__global__ void __launch_bounds__(128, 4) k2f_x2(const Params p) {
+    typedef FwdX2<K> W;
+    enum { K4 = W::K4 };
+    GOTOH_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* my_smem = smem_raw + (size_t)warp * Smem<K>::per_warp(p.l);
+    uint4* prof = reinterpret_cast<uint4*>(my_smem);
+    W w;
+    w.lane = lane;
+    w.u = p.u; w.v = p.v;
+    w.inf16 = p.inf16; w.S = p.shift16;
+    w.v2 = pk2(p.v, p.v); w.negu2 = pk2(-p.u, -p.u);
+    w.c_nn = 65536u;
+    w.c_nr = lin2(1 - p.v, 1 - p.v) + 65536u;
+    w.one = p.two >> 1; w.two = p.two; w.four = p.four; w.neg1 = p.neg1;
+    w.prof_lane = prof + lane;
+    w.keep = (p.two >> 1) - (lane == 0 ? 1u : 0u);
+    w.injq = lane == 0 ? pk2(p.inf16, p.inf16) : 0u;
+    const int e_pad = p.v + 1;                            // padding columns: diag' = R'(i-1,N) + v + 1 > R'(i,N), never wins
+
+    for (;;) {
+        unsigned tsk = 0;
+        if (lane == 0) tsk = atomicAdd(p.counter_f, 1u);
+        tsk = __shfl_sync(0xffffffffu, tsk, 0);
+        if (tsk >= (unsigned)p.task_count) break;
+        const StripTask task = p.tasks[tsk];
+        const int ia = task.pair, ib = task.strip >= 0 ? task.strip : task.pair;
+        const PairInfo pa = p.pairs[ia];
+        const PairInfo pb = p.pairs[ib];
+        const int M = pa.M, Na = pa.N, Nb = pb.N, nblk = pa.nblk;
+        const uint8_t* sa = p.s2_idx + pa.qry_pos;
+        const uint8_t* sb = p.s2_idx + pb.qry_pos;
+        const int j0 = lane * K;
+        w.M = M; w.Na = Na; w.Nb = Nb; w.j0 = j0;
+        w.cls = p.s1_idx + pa.ref_pos;
+        w.row_min_a = w.row_min_b = 2147483647; w.row_j_a = w.row_j_b = 0; w.r_ll_a = w.r_ll_b = 0;
+        // column 0 in the shifted frame: R'(i,0) = v - S (global) or -i*u - S (local)
+        w.c0run = lane == 0 ? (p.is_global ? pk2(p.v - p.shift16, p.v - p.shift16) : pk2(-p.shift16, -p.shift16)) : 0u;
+        w.c0step = (lane == 0 && !p.is_global) ? pk2(-p.u, -p.u) : 0u;
+
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) w.vq[k] = pk2((j0 + k) < Na ? p.v : 0, (j0 + k) < Nb ? p.v : 0);
+        for (int c = 0; c < p.l; ++c) {
+            const int32_t* drow = p.dmat + c * p.l;
+#pragma unroll
+            for (int kq = 0; kq < K4; ++kq) {
+                unsigned e[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = kq * 4 + kk, ja = j0 + k;
+                    int ea = e_pad, eb = e_pad;
+                    if (k < K && ja < Na) ea = -drow[sa[ja]] - 2 * p.u;
+                    if (k < K && ja < Nb) eb = -drow[sb[ja]] - 2 * p.u;
+                    e[kk] = lin2(ea, eb);
+                }
+                prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
+            }
+        }
+        __syncwarp();
+        w.sendR = 0; w.sendQ = 0;
+        w.wlo_a = w.whi_a = w.wlo_b = w.whi_b = make_uint4(0, 0, 0, 0);
+        w.row0_init(p.is_global);
+        w.next_cls = w.cls[-lane];
+
+        uint4* dlo_a = p.lo + pa.dir_off + lane;
+        uint4* dhi_a = p.hi + pa.dir_off + lane;
+        uint4* dlo_b = p.lo + pb.dir_off + lane;
+        uint4* dhi_b = p.hi + pb.dir_off + lane;
+        const bool two_pairs = task.strip >= 0;
+        for (int tb = 0; tb < nblk; ++tb) {
+            const int t0 = tb * FSTEPS + 1, hi = t0 + FSTEPS - 1;
+            const bool slow = (t0 <= 31) || (hi >= M);
+            if (slow) {
+#pragma unroll
+                for (int s = 0; s < FSTEPS; ++s) w.template step<true>(t0 + s, s, p.is_global);
+            } else {
+#pragma unroll
+                for (int s = 0; s < FSTEPS; ++s) w.template step<false>(t0 + s, s, p.is_global);
+            }
+            dlo_a[(int64_t)tb * 32] = w.wlo_a; dhi_a[(int64_t)tb * 32] = w.whi_a;
+            if (two_pairs) { dlo_b[(int64_t)tb * 32] = w.wlo_b; dhi_b[(int64_t)tb * 32] = w.whi_b; }
+        }
+
+        // ---- start cells (_gotoh2.c:327-352), per half ------------------------------------------------------
+        const int i_fin = nblk * FSTEPS - lane;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (half == 1 && !two_pairs) break;
+            const int N = half ? Nb : Na;
+            int row_min = half ? w.row_min_b : w.row_min_a, row_j = half ? w.row_j_b : w.row_j_a;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const int om = __shfl_xor_sync(0xffffffffu, row_min, off);
+                const int oj = __shfl_xor_sync(0xffffffffu, row_j, off);
+                if (om < row_min || (om == row_min && oj < row_j)) { row_min = om; row_j = oj; }
+            }
+            const int owner = ((N - 1) / K) & 31;
+            int col_min = (half ? hi16(w.bf) : lo16(w.bf)) + (i_fin + N) * p.u + p.shift16;
+            col_min = __shfl_sync(0xffffffffu, col_min, owner);
+            const int col_i = __shfl_sync(0xffffffffu, half ? w.best_i_b : w.best_i_a, owner);
+            const int r_ll = __shfl_sync(0xffffffffu, half ? w.r_ll_b : w.r_ll_a, owner);
+            if (lane == 0) {
+                int best = r_ll, bi = M, bj = N;
+                if (!p.is_global) {
+                    if (col_min < best) { best = col_min; bi = col_i; bj = N; }
+                    int rm = 0, rj = 0;                          // R(l1, 0) = 0 in local mode (_gotoh2.c:111)
+                    if (row_min < rm) { rm = row_min; rj = row_j; }
+                    if (rm < best) { best = rm; bi = M; bj = rj; }
+                }
+                const int pi = half ? ib : ia;
+                p.best[pi] = best;
+                p.start_i[pi] = bi;
+                p.start_j[pi] = bj;
+            }
         }
     }
 }

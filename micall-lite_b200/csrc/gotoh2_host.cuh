@@ -8,7 +8,7 @@
 namespace {
 
 // stats of this thread's last gotoh2 call (gotoh_b200_gotoh2_last_stats)
-thread_local double g2_stats[10] = {0};
+thread_local double g2_stats[11] = {0};
 
 struct G2Events {
     cudaEvent_t e[5] = {0, 0, 0, 0, 0};
@@ -66,6 +66,8 @@ struct G2Run {
     double ms_f = 0, ms_r = 0, ms_w = 0;
     int launches = 0, chunks = 0;
     int64_t arena_bytes = 0;
+    int64_t pairs_x2 = 0;           // forward tasks that ran as int16x2 couples
+    const int32_t* h_dmat = nullptr;
 };
 
 // k_emit + the per-chunk timing bookkeeping shared by both kernel families
@@ -167,6 +169,19 @@ int g2_launch_fwd(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
     CU(cudaGetLastError());
     return 0;
 }
+template <int K>
+int g2_launch_fwd_x2(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
+    using namespace gotoh::g2f;
+    const size_t per_warp = Smem<K>::per_warp(run.l);
+    const size_t smem = per_warp * 4;
+    if (smem > 220 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
+    CU(cudaFuncSetAttribute(k2f_x2<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
+    const int grid = std::max(1, std::min((ntasks + 3) / 4, run.sm_count * ctas_per_sm));
+    GOTOH_LAUNCH((k2f_x2<K>), dim3(grid), dim3(128), smem, (cudaStream_t)0, p);
+    CU(cudaGetLastError());
+    return 0;
+}
 template <int K, bool MULTI>
 int g2_launch_rev(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
     using namespace gotoh::g2f;
@@ -177,6 +192,7 @@ int g2_launch_rev(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
 }
 template <int K>
 int g2_launch_group(G2Run& run, const gotoh::g2f::Params& p, int ntasks, bool multi, int phase) {
+    if (phase == 2) return g2_launch_fwd_x2<K>(run, p, ntasks);
     if (phase == 0) {
         if (run.score_only) return multi ? g2_launch_fwd<K, true, false>(run, p, ntasks) : g2_launch_fwd<K, false, false>(run, p, ntasks);
         return multi ? g2_launch_fwd<K, true, true>(run, p, ntasks) : g2_launch_fwd<K, false, true>(run, p, ntasks);
@@ -184,10 +200,28 @@ int g2_launch_group(G2Run& run, const gotoh::g2f::Params& p, int ntasks, bool mu
     return multi ? g2_launch_rev<K, true>(run, p, ntasks) : g2_launch_rev<K, false>(run, p, ntasks);
 }
 
+// k2f_x2 admits a pair when every value of its grid in the frame X' = X - (i+j)*u - S, every difference the tie codes
+// take and the "+infinity" stay inside 16 bits without wrapping (the adds of VIADDMNMX.S16x2 wrap).  With
+// dmax = max(0, max d), gap costs >= 0 and at most min(l1,l2) diagonal steps: X~ >= -(dmax*min(l1,l2) + (l1+l2+40)*u)
+// =: -L (40 rows of wavefront fill/drain are swept too), R~ <= 2v, p~, q~ <= 3v.  S = 4v + max(0,-dmin) + 8 makes every
+// R' and every diagonal candidate negative and every negated value positive (see the kernel); "+infinity" is
+// 3v + 16 - S.  Largest sum formed: a diagonal candidate minus the smallest R' < L + 4v - dmin; smallest value:
+// -L - S - dmax - 2u.
+inline int g2_shift16(int gop, int dmin) { return 4 * gop + std::max(0, -dmin) + 8; }
+inline int g2_inf16(int gop, int dmin) { return 3 * gop + 16 - g2_shift16(gop, dmin); }
+inline bool g2_fits_int16(int M, int N, int gop, int gep, int dmax, int dmin) {
+    const long long L = (long long)std::max(0, dmax) * std::min(M, N) + (long long)(M + N + 40) * gep;
+    return L + 5LL * gop + 2LL * std::max(0, -dmin) + std::max(0, dmax) + 2LL * gep + 64 <= 32000;
+}
+
 int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
     using namespace gotoh::g2f;
     const size_t n = (size_t)run.n;
     static const int kK[] = {2, 3, 4, 6, 8};
+    // forward in int16x2 (two pairs that share seq1 per warp) wherever the range proof holds; GOTOH_B200_GOTOH2=x1
+    // pins the int32 forward kernel for tests (still a GPU path)
+    const char* g2sel = getenv("GOTOH_B200_GOTOH2");
+    const bool use_x2 = !run.score_only && !(g2sel && !strcmp(g2sel, "x1"));
     // ---- geometry per pair: K columns per lane, strips, blocks; chunks by arena budget ----------------------
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
@@ -227,23 +261,29 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
     chunks.push_back({first, (int)(n - first), slots, bnd});
     if (!run.score_only) { CU(b.lo.ensure((size_t)arena_max)); CU(b.hi.ensure((size_t)arena_max)); }
     CU(b.extra.ensure(n));
-    CU(b.tasks.ensure((size_t)slots_max));
+    CU(b.tasks.ensure((size_t)slots_max * 2 + 8));
     CU(b.prog.ensure((size_t)slots_max * 2 + 2));
     CU(b.part.ensure((size_t)slots_max * 2));
     CU(b.fbnd.ensure((size_t)bnd_max + 1));
     CU(b.rbnd.ensure((size_t)bnd_max + 1));
-    CU(b.counters.ensure(16));
+    CU(b.counters.ensure(24));
     CU(cudaMemcpy(b.pairs.p, pairs.data(), n * sizeof(PairInfo), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(b.extra.p, extra.data(), n * sizeof(Extra), cudaMemcpyHostToDevice));
     run.arena_bytes = run.score_only ? 0 : arena_max * 32;
     run.chunks = (int)chunks.size();
 
+    int dmax = 0, dmin = 0;
+    for (int x = 0; x < run.l * run.l; ++x) { dmax = std::max(dmax, (int)run.h_dmat[x]); dmin = std::min(dmin, (int)run.h_dmat[x]); }
     std::vector<StripTask> tasks;
     for (const auto& ch : chunks) {
-        // groups: (K, single strip) and (8, multi strip); tasks of one group are contiguous in b.tasks
-        struct Group { int K; bool multi; int first, count; };
+        // groups: (K, single strip) and (8, multi strip); tasks of one group are contiguous in b.tasks.  The reverse sweep
+        // takes every (pair, strip) of the group; the forward sweep takes the same list (int32) unless some pairs of a
+        // single-strip group run in int16x2, in which case it gets its own int32 list and a list of pair couples.
+        struct Group { int K; bool multi; int first, count, f32_first, f32_count, x2_first, x2_count; };
         std::vector<Group> groups;
         tasks.clear();
+        std::vector<StripTask> f32, fx2;
+        std::unordered_map<int64_t, int> open_couple;          // ref_pos -> index into fx2 of a task that still lacks its second pair
         for (int gi = 0; gi < 6; ++gi) {
             const int K = gi < 5 ? kK[gi] : 8;
             const bool multi = (gi == 5);
@@ -259,36 +299,62 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
                     if (pairs[(size_t)k].K != K || (extra[(size_t)k].nstrips > 1) != multi || s >= extra[(size_t)k].nstrips) continue;
                     tasks.push_back({k, s});
                 }
-            if ((int)tasks.size() > t0) groups.push_back({K, multi, t0, (int)tasks.size() - t0});
+            if ((int)tasks.size() == t0) continue;
+            Group g = {K, multi, t0, (int)tasks.size() - t0, t0, (int)tasks.size() - t0, 0, 0};
+            if (use_x2 && !multi) {
+                f32.clear(); fx2.clear(); open_couple.clear();
+                for (int x = t0; x < (int)tasks.size(); ++x) {
+                    const PairInfo& pi = pairs[(size_t)tasks[(size_t)x].pair];
+                    if (!g2_fits_int16(pi.M, pi.N, run.gop, run.gep, dmax, dmin)) { f32.push_back(tasks[(size_t)x]); continue; }
+                    auto it = open_couple.find(pi.ref_pos);
+                    if (it != open_couple.end()) { fx2[(size_t)it->second].strip = tasks[(size_t)x].pair; open_couple.erase(it); }
+                    else { open_couple[pi.ref_pos] = (int)fx2.size(); fx2.push_back({tasks[(size_t)x].pair, -1}); }
+                }
+                if (!fx2.empty()) {
+                    g.f32_first = (int)tasks.size(); g.f32_count = (int)f32.size();
+                    tasks.insert(tasks.end(), f32.begin(), f32.end());
+                    g.x2_first = (int)tasks.size(); g.x2_count = (int)fx2.size();
+                    tasks.insert(tasks.end(), fx2.begin(), fx2.end());
+                }
+            }
+            groups.push_back(g);
         }
         CU(cudaMemcpy(b.tasks.p, tasks.data(), tasks.size() * sizeof(StripTask), cudaMemcpyHostToDevice));
         CU(cudaMemset(b.prog.p, 0, (size_t)ch.slots * sizeof(int32_t)));                       // forward: rows published
         CU(cudaMemset(b.prog.p + slots_max, 0x7f, ((size_t)ch.slots + 2) * sizeof(int32_t)));  // reverse: lowest row done
-        CU(cudaMemset(b.counters.p, 0, 16 * sizeof(uint32_t)));
+        CU(cudaMemset(b.counters.p, 0, 24 * sizeof(uint32_t)));
         Params p;
         memset(&p, 0, sizeof(p));
         p.pairs = b.pairs.p; p.extra = b.extra.p;
         p.s1_idx = b.idx1.p; p.s2_idx = b.idx2.p; p.dmat = b.dmat.p;
         p.l = run.l; p.v = run.gop; p.u = run.gep; p.is_global = run.is_global;
         p.two = 2; p.four = 4; p.neg1 = 0xffffffffu;
+        p.inf16 = g2_inf16(run.gop, dmin); p.shift16 = g2_shift16(run.gop, dmin);
         p.lo = b.lo.p; p.hi = b.hi.p; p.bnd = b.fbnd.p; p.rbnd = b.rbnd.p;
         p.prog_f = b.prog.p; p.prog_r = b.prog.p + slots_max;
         p.part_min = b.part.p; p.part_j = b.part.p + slots_max;
         p.best = b.best.p; p.start_i = b.si.p; p.start_j = b.sj.p;
         CU(cudaEventRecord(run.ev.e[0], 0));
         for (size_t g = 0; g < groups.size(); ++g) {
-            p.tasks = b.tasks.p + groups[g].first; p.task_count = groups[g].count;
-            p.counter_f = b.counters.p + g;
-            int rc = 0;
-            switch (groups[g].K) {
-                case 2: rc = g2_launch_group<2>(run, p, groups[g].count, groups[g].multi, 0); break;
-                case 3: rc = g2_launch_group<3>(run, p, groups[g].count, groups[g].multi, 0); break;
-                case 4: rc = g2_launch_group<4>(run, p, groups[g].count, groups[g].multi, 0); break;
-                case 6: rc = g2_launch_group<6>(run, p, groups[g].count, groups[g].multi, 0); break;
-                default: rc = g2_launch_group<8>(run, p, groups[g].count, groups[g].multi, 0); break;
+            for (int pass = 0; pass < 2; ++pass) {             // pass 0: int16x2 couples, pass 1: int32 tasks
+                const int first = pass == 0 ? groups[g].x2_first : groups[g].f32_first;
+                const int count = pass == 0 ? groups[g].x2_count : groups[g].f32_count;
+                if (count == 0) continue;
+                p.tasks = b.tasks.p + first; p.task_count = count;
+                p.counter_f = b.counters.p + (pass == 0 ? 16 : 0) + g;
+                const int phase = pass == 0 ? 2 : 0;
+                int rc = 0;
+                switch (groups[g].K) {
+                    case 2: rc = g2_launch_group<2>(run, p, count, groups[g].multi, phase); break;
+                    case 3: rc = g2_launch_group<3>(run, p, count, groups[g].multi, phase); break;
+                    case 4: rc = g2_launch_group<4>(run, p, count, groups[g].multi, phase); break;
+                    case 6: rc = g2_launch_group<6>(run, p, count, groups[g].multi, phase); break;
+                    default: rc = g2_launch_group<8>(run, p, count, groups[g].multi, phase); break;
+                }
+                if (rc) return rc;
+                ++run.launches;
+                if (pass == 0) run.pairs_x2 += count;
             }
-            if (rc) return rc;
-            ++run.launches;
         }
         CU(cudaEventRecord(run.ev.e[1], 0));
         if (!run.score_only) {
@@ -477,7 +543,7 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
 
     G2Run run;
     run.n = n_pairs; run.l = l; run.gop = gop; run.gep = gep; run.is_global = is_global ? 1 : 0;
-    run.score_only = score_only; run.sm_count = prop.multiProcessorCount; run.max_rows = max_rows;
+    run.score_only = score_only; run.sm_count = prop.multiProcessorCount; run.max_rows = max_rows; run.h_dmat = matrix;
     if (!run.ev.create()) return fail(GOTOH_B200_ECUDA, "cudaEventCreate failed");
     const char* force = getenv("GOTOH_B200_GOTOH2");          // tests: "general" pins the un-tuned kernels (still a GPU path)
     const bool fast = gop >= 0 && gep >= 0 && !(force && !strcmp(force, "general"));
@@ -489,6 +555,7 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
     g2_stats[4] = run.ms_w; g2_stats[5] = run.launches; g2_stats[6] = (double)run.arena_bytes; g2_stats[7] = (double)run.chunks;
     g2_stats[8] = (double)(h_raw1.size() * 2 + h_raw2.size() * 2 + n * sizeof(PairInfo) + (size_t)l * l * 4);
     g2_stats[9] = (double)((score_only ? 0 : 2 * out_bytes) + 8 * (int64_t)n);
+    g2_stats[10] = (double)run.pairs_x2;
     if (score_only) {
         CU(cudaMemcpy(out_score, b.best.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
         for (int64_t k = 0; k < n_pairs; ++k) out_score[k] = -out_score[k];
@@ -508,8 +575,8 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
 
 extern "C" int32_t gotoh_b200_gotoh2_last_stats(double* out, int32_t n) {
     if (!out || n < 0) return fail(GOTOH_B200_EINVAL, "NULL argument");
-    for (int x = 0; x < n && x < 10; ++x) out[x] = g2_stats[x];
-    return n < 10 ? n : 10;
+    for (int x = 0; x < n && x < 11; ++x) out[x] = g2_stats[x];
+    return n < 11 ? n : 11;
 }
 
 extern "C" int32_t gotoh_b200_gotoh2_align_batch(const uint8_t* s1_bytes, const int64_t* s1_off, int64_t n_s1,

@@ -211,6 +211,16 @@ static inline unsigned __vibmax_s16x2(unsigned a, unsigned b, bool* phi, bool* p
     return __vmaxs2(a, b);
 }
 static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vadd2(a, b), c); }
+static inline unsigned __vmins2(unsigned a, unsigned b) {
+    return simt_pack(min((int)simt_lo(a), (int)simt_lo(b)), min((int)simt_hi(a), (int)simt_hi(b)));
+}
+static inline unsigned __viaddmin_s16x2(unsigned a, unsigned b, unsigned c) { return __vmins2(__vadd2(a, b), c); }
+static inline unsigned __viaddmin_s16x2_relu(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vmins2(__vadd2(a, b), c), 0u); }
+static inline unsigned __vimin3_s16x2(unsigned a, unsigned b, unsigned c) { return __vmins2(__vmins2(a, b), c); }
+static inline unsigned __vibmin_s16x2(unsigned a, unsigned b, bool* phi, bool* plo) {
+    *plo = simt_lo(a) <= simt_lo(b); *phi = simt_hi(a) <= simt_hi(b);
+    return __vmins2(a, b);
+}
 static inline unsigned __vimax3_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vmaxs2(a, b), c); }
 
 // ---- kernel launch -------------------------------------------------------------------

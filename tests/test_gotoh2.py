@@ -105,6 +105,65 @@ def test_emu_gotoh2_general_kernels_still_match(emu_aligner, monkeypatch):
     assert n >= 300 and not bad, bad[:5]
 
 
+def _couple_cases(n_reads, seed):
+    """Many second sequences of ragged length against a shared first sequence: the int16x2 forward kernel couples
+    them two per warp (k2f_x2); widths cover every K group, the last read of a group stays single."""
+    from gotoh_b200 import workloads
+    rng = random.Random(seed)
+    ref, reads = workloads.c2_reads(n_reads, seed=seed)
+    sub = ref[500:1100]
+    nt = [(sub, r[:rng.choice([251, 250, 200, 130, 97, 64, 33, 17, 5, 1])]) for r in reads]
+    nt += [(ref[1000:1300], r[:rng.randint(1, 251)]) for r in reads[:n_reads // 3]]
+    refs, qs = workloads.c3_queries(n_reads, seed=seed + 1)
+    aa = [(refs[k % 3], q[:rng.randint(1, len(q))]) for k, q in enumerate(qs)]
+    return ref, reads, nt, aa
+
+
+def _x2_tasks(lib):
+    import ctypes
+    stats = (ctypes.c_double * 11)()
+    assert lib.lib.gotoh_b200_gotoh2_last_stats(stats, 11) == 11
+    return int(stats[10])
+
+
+def _check_couples(lib, oracle2, monkeypatch, n_reads, n_full):
+    from gotoh_b200.gotoh2 import Aligner
+    ref, reads, nt, aa = _couple_cases(n_reads, 3)
+    jobs = [(nt, g, e, glob, "HYPHY_NUC") for g, e, glob in [(10, 3, False), (15, 3, True), (0, 0, True), (2, 1, False), (0, 1, True)]]
+    jobs += [(aa, g, e, glob, "EmpHIV25") for g, e, glob in [(40, 10, False), (40, 10, True), (3, 1, False)]]
+    # full-length first sequence (3039 rows): ordinary read settings, penalties close to the 16-bit range limit
+    # (admitted), and just past it (must fall back to the int32 forward kernel)
+    full = [(ref, r) for r in reads[:n_full]]
+    jobs += [(full, 10, 3, False, "HYPHY_NUC"), (full, 10, 9, True, "HYPHY_NUC"), (full, 300, 8, False, "HYPHY_NUC")]
+    for pairs, gop, gep, glob, model in jobs:
+        al = Aligner(gop, gep, glob, model, library=lib)
+        out = al.align_batch(pairs)
+        assert _x2_tasks(lib) >= len(pairs) // 2 - 8, (gop, gep, glob, model)
+        for (a, b), o in zip(pairs, out):
+            assert o == oracle2.align(a, b, gop, gep, glob, model), (gop, gep, glob, model, b)
+    al = Aligner(10, 10, False, "HYPHY_NUC", library=lib)
+    out = al.align_batch(full)
+    assert _x2_tasks(lib) == 0
+    for (a, b), o in zip(full, out):
+        assert o == oracle2.align(a, b, 10, 10, False, "HYPHY_NUC")
+    # GOTOH_B200_GOTOH2=x1 pins the int32 forward kernel: same answers, no couples
+    monkeypatch.setenv("GOTOH_B200_GOTOH2", "x1")
+    al = Aligner(10, 3, False, "HYPHY_NUC", library=lib)
+    out = al.align_batch(nt)
+    assert _x2_tasks(lib) == 0
+    for (a, b), o in zip(nt, out):
+        assert o == oracle2.align(a, b, 10, 3, False, "HYPHY_NUC")
+
+
+def test_emu_gotoh2_int16x2_couples(emu_aligner, oracle2_port, monkeypatch):
+    _check_couples(emu_aligner._libobj, oracle2_port, monkeypatch, n_reads=36, n_full=4)
+
+
+@pytest.mark.gpu
+def test_gpu_gotoh2_int16x2_couples(gpu_aligner, oracle2_port, monkeypatch):
+    _check_couples(gpu_aligner._libobj, oracle2_port, monkeypatch, n_reads=900, n_full=40)
+
+
 @pytest.mark.gpu
 def test_gpu_gotoh2_golden_incl_reference_unit_tests(gpu_aligner):
     from gotoh_b200.gotoh2 import Aligner

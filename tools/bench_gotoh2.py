@@ -59,7 +59,7 @@ def run(name, pairs, gop, gep, glob, model, steps, verify, cpu_seconds):
     from oracle.oracle2 import Oracle2
     al = Aligner(gop, gep, glob, model)
     lib = al._libobj.lib
-    stats = (ctypes.c_double * 10)()
+    stats = (ctypes.c_double * 11)()
     best = None
     e2e = []
     out = None
@@ -67,7 +67,7 @@ def run(name, pairs, gop, gep, glob, model, steps, verify, cpu_seconds):
         t0 = time.perf_counter()
         out = al.align_batch(pairs)
         dt = time.perf_counter() - t0
-        lib.gotoh_b200_gotoh2_last_stats(stats, 10)
+        lib.gotoh_b200_gotoh2_last_stats(stats, 11)
         s = list(stats)
         if it == 0:
             continue                      # warm-up
@@ -105,7 +105,7 @@ def run(name, pairs, gop, gep, glob, model, steps, verify, cpu_seconds):
             "alignments_per_s": len(pairs) / (best[1] * 1e-3), "ms_kernels": best[1], "ms_forward": best[2],
             "ms_reverse": best[3], "ms_walk_emit": best[4], "gcups_forward": cells / (best[2] * 1e-3) / 1e9,
             "gcups_reverse": cells / (best[3] * 1e-3) / 1e9, "gpu_launches": best[5], "arena_bytes": best[6],
-            "chunks": best[7], "e2e_gcups_c_abi": cells / min(cabi) / 1e9, "e2e_s_c_abi": min(cabi),
+            "chunks": best[7], "forward_tasks_int16x2": best[10], "e2e_gcups_c_abi": cells / min(cabi) / 1e9, "e2e_s_c_abi": min(cabi),
             "h2d_bytes": best[8], "d2h_bytes": best[9], "e2e_gcups_python_api": cells / min(e2e) / 1e9, "verified": len(idx), "mismatches": bad,
             "params": {"gop": gop, "gep": gep, "is_global": glob, "model": model}}
     if cpu_seconds > 0:

@@ -11,6 +11,6 @@ $CMD > gpurun_out/gotoh2_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/gotoh2_launches.csv $CMD > gpurun_out/gotoh2_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"; tail -2 gpurun_out/gotoh2_plain.log
 $CMD > gpurun_out/gotoh2_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'^k2f$|^k2r$' -s 2 -c 2 -f -o gpurun_out/prof_gotoh2 $CMD > gpurun_out/gotoh2_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'^k2f_x2$|^k2f$|^k2r$' -s 2 -c 2 -f -o gpurun_out/prof_gotoh2 $CMD > gpurun_out/gotoh2_ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -3 gpurun_out/gotoh2_ncu_full.log
 fi

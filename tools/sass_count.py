@@ -110,10 +110,10 @@ def main():
            "instr_per_cell_x2": x2["instr_per_cell"], "alu_per_cell_x2": x2["alu_per_cell"], "fma_per_cell_x2": x2["fma_per_cell"],
            "instr_per_cell_x1": x1["instr_per_cell"], "alu_per_cell_x1": x1["alu_per_cell"], "fma_per_cell_x1": x1["fma_per_cell"]}
     # gotoh2 (live aligner) kernels: forward with tie bits, score-only forward, reverse sweep (4 lane-steps x 8 columns)
-    for tag, pat, sh, per in (("g2_forward", "k2fILi8ELb0ELb1", "SHFL.UP", 2), ("g2_forward_score_only", "k2fILi8ELb0ELb0", "SHFL.UP", 2),
-                              ("g2_reverse", "k2rILi8ELb0", "SHFL.DOWN", 1)):
+    for tag, pat, sh, per, npair in (("g2_forward", "k2fILi8ELb0ELb1", "SHFL.UP", 2, 1), ("g2_forward_score_only", "k2fILi8ELb0ELb0", "SHFL.UP", 2, 1),
+                                     ("g2_forward_x2", "k2f_x2ILi8E", "SHFL.UP", 2, 2), ("g2_reverse", "k2rILi8ELb0", "SHFL.DOWN", 1, 1)):
         try:
-            doc[tag] = count(pat, 4, 8, 1, sh, per)
+            doc[tag] = count(pat, 4, 8, npair, sh, per)
         except Exception as e:      # a kernel without a 128-bit store in its loop (score-only) has no such block
             doc[tag] = {"error": str(e)}
     prev = os.path.join(ROOT, "profiles", "sass_counts.json")
@@ -127,7 +127,7 @@ def main():
             pass
     os.makedirs(os.path.dirname(prev), exist_ok=True)
     json.dump(doc, open(prev, "w"), indent=1)
-    for tag in ("x2", "x1", "g2_forward", "g2_forward_score_only", "g2_reverse"):
+    for tag in ("x2", "x1", "g2_forward", "g2_forward_score_only", "g2_forward_x2", "g2_reverse"):
         d = doc[tag]
         if "error" in d:
             print(tag, d["error"])
