@@ -197,6 +197,7 @@ struct gotoh_b200_plan {
     int ncls = 1;
     int has_dollar = 0;
     int smin_m1 = 0;
+    int zshift = 0;        // Vec16 frame shift (fits_int16)
     std::vector<Chunk> chunks;
     int n_launches = 0;
     int64_t out_base = 0, out_bytes = 0;   // caller's out_off range covered by this plan
@@ -233,17 +234,24 @@ int pick_K(int n) {
 
 // "range proof" for the int16x2 path: with rebase period R every value the Vec16 kernel
 // forms for real cells stays inside int16.  All quantities in stored units.
-bool fits_int16(int M, int N, int K, int R, int gip, int gep, int minT, int maxT) {
+// The stored frame is shifted up by z4 (a multiple of 4, one per plan) so that no stored S^ and no diagonal
+// candidate D^ is negative: the kernel then adds the packed substitution scores with one 32-bit multiply-add
+// (DESIGN.md 3.5b).  int16_low_need() is the smallest such shift for a pair.
+long long int16_low_need(int M, int N, int gip, int gep, int minT) {
+    const long long mn = std::min(M, N);
+    const long long smin = (long long)std::min(minT, 0) * mn;
+    const long long vmin = 4 * (smin - 2LL * gip - gep) - 8;
+    const long long add_lo = 4LL * std::max<long long>(gip, -(long long)std::min(minT, 0)) + 8;
+    return ((-(vmin - add_lo)) + 3) & ~3LL;
+}
+bool fits_int16(int M, int N, int K, int R, int gip, int gep, int minT, int maxT, long long z4) {
     const long long mn = std::min(M, N);
     const long long smax = (long long)std::max(maxT, 0) * mn;
-    const long long smin = (long long)std::min(minT, 0) * mn;
     const long long g = gep;
     const long long vmax = 4 * (smax + (R + 32LL * K + 2) * g) + 8;
-    const long long vmin = 4 * (smin - 2LL * gip - gep) - 8;
     const long long add_hi = 4 * (std::max(maxT, 0) + 2 * g) + 4;
-    const long long add_lo = 4LL * std::max<long long>(gip, -(long long)std::min(minT, 0)) + 8;
-    if (vmax + add_hi > 32000) return false;
-    if (vmin - add_lo < -32000) return false;
+    if (vmax + add_hi + z4 > 32000) return false;
+    if (int16_low_need(M, N, gip, gep, minT) > z4) return false;
     if (4LL * R * g > 30000) return false;   // the rebase delta itself must be an int16
     return true;
 }
@@ -562,11 +570,20 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     std::vector<KeyIdx> elig, wide;
     elig.reserve((size_t)n);
     int worstM = 0, worstN = 0;   // for picking R: fits_int16 is monotone in min(M,N) and K
+    // the plan's frame shift: the largest need among the pairs that would fit with their own shift
+    long long z4 = 0;
+    if (force != 32)
+        for (const HostPair& h : hp) {
+            if (h.N > 32 * kMaxK) continue;
+            const long long need = int16_low_need(h.M, h.N, pl->gip, pl->gep, minT);
+            if (fits_int16(h.M, h.N, pick_K(h.N), 32, pl->gip, pl->gep, minT, maxT, need)) z4 = std::max(z4, need);
+        }
+    pl->zshift = (int)z4;
     for (size_t x = 0; x < hp.size(); ++x) {
         const HostPair& h = hp[x];
         const int K = pick_K(h.N);
         const bool ok = h.N <= 32 * kMaxK && force != 32 && nu < (1u << 26) &&
-                        fits_int16(h.M, h.N, K, 32, pl->gip, pl->gep, minT, maxT);
+                        fits_int16(h.M, h.N, K, 32, pl->gip, pl->gep, minT, maxT, z4);
         KeyIdx ki;
         ki.idx = (uint32_t)x;
         if (ok) {
@@ -587,7 +604,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
             bool all = true;
             for (const KeyIdx& ki : elig) {
                 const HostPair& h = hp[ki.idx];
-                if (!fits_int16(h.M, h.N, pick_K(h.N), cand, pl->gip, pl->gep, minT, maxT)) { all = false; break; }
+                if (!fits_int16(h.M, h.N, pick_K(h.N), cand, pl->gip, pl->gep, minT, maxT, z4)) { all = false; break; }
             }
             if (all) { R = cand; break; }
         }
@@ -813,7 +830,7 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
             fp.ncls = pl->ncls; fp.gip = pl->gip; fp.gep = pl->gep;
             fp.has_dollar = pl->has_dollar;
             fp.bonus4 = ws->d_table4.p + (size_t)pl->ncls * 128;
-            fp.rebase_mask = L.rebase_mask; fp.smin_m1 = pl->smin_m1;
+            fp.rebase_mask = L.rebase_mask; fp.smin_m1 = pl->smin_m1; fp.zshift = pl->zshift;
             fp.four = 4u;
             fp.dir = ws->d_dir.p;
             fp.bnd = L.multi_strip ? ws->d_bnd.p : nullptr; fp.bnd_stride = pl->bnd_stride;
@@ -915,7 +932,7 @@ int check_common(const void* ref_bytes, const int64_t* ref_off, int64_t n_refs, 
 // ---- cached per-device contexts for the one-shot call: four workspaces = four slabs in flight ----
 // (two being packed by the two builder threads, one in its kernels, one copying back; with two, the host could not start packing
 // slab s+1 before slab s-1 had finished its D2H and the kernels idled ~30 % of the time - measured on B200)
-enum { NWS = 4, NBUILD = 2 };
+enum { NWS = 8, NBUILD = 4 };
 struct DeviceCtx {
     std::mutex mu;
     Workspace ws[NWS];
@@ -939,18 +956,23 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     DeviceCtx* ctx = ctx_for(dev);
     if (!ctx) return fail(GOTOH_B200_ENOMEM, "out of host memory");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    for (int w = 0; w < NWS; ++w) { const int rc = ctx->ws[w].init(dev); if (rc) return rc; }
+    // workspaces in flight (GOTOH_B200_WORKSPACES, default 8) and builder threads (GOTOH_B200_BUILDERS, default 2).  B200
+    // trace with 4 workspaces: each builder spent half its time waiting for the workspace it was about to reuse while the
+    // GPU idled 22 % of the call - a builder must be able to run several slabs ahead of the kernels.
+    int nws = getenv("GOTOH_B200_WORKSPACES") ? atoi(getenv("GOTOH_B200_WORKSPACES")) : 8;
+    nws = std::max(1, std::min(nws, (int)NWS));
+    for (int w = 0; w < nws; ++w) { const int rc = ctx->ws[w].init(dev); if (rc) return rc; }
     CU(cudaSetDevice(dev));
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     int64_t cached = 0;
     for (int w = 0; w < NWS; ++w) cached += (int64_t)ctx->ws[w].d_dir.cap * 16;
     // small slabs keep the pipeline's fill and drain short (first packing, last D2H); 3 GB of arena = ~16 k reads
-    int64_t slab_budget = std::min<int64_t>(((int64_t)free_b + cached) / (NWS + 2), (int64_t)3 << 30);
+    int64_t slab_budget = std::min<int64_t>(((int64_t)free_b + cached) / (nws + 2), (int64_t)3 << 30);
     slab_budget = std::max<int64_t>(slab_budget, (int64_t)256 << 20);
     if (getenv("GOTOH_B200_SLAB_MB")) slab_budget = (int64_t)atoll(getenv("GOTOH_B200_SLAB_MB")) << 20;   // tests
     gotoh_b200_plan plans[NWS];
-    for (int w = 0; w < NWS; ++w) {
+    for (int w = 0; w < nws; ++w) {
         plans[w].ws = &ctx->ws[w];
         plans[w].gip = gip; plans[w].gep = gep; plans[w].term = term ? 1 : 0; plans[w].matrix = matrix_id;
         plans[w].arena_budget_bytes = slab_budget;
@@ -977,8 +999,8 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     if (trace_on()) { cudaEventRecord(ctx->ws[0].ev[3], ctx->ws[0].stream); cudaEventSynchronize(ctx->ws[0].ev[3]); for (int w = 0; w < NWS; ++w) ctx->ws[w].trace_slab = -1; }
     // Two builder threads pack alternate slabs (each owns half of the workspaces), so the host's packing rate is
     // not the pipeline's bottleneck: per slab the host needs about as long as the kernels (measured on B200).
-    int builders = getenv("GOTOH_B200_BUILDERS") ? atoi(getenv("GOTOH_B200_BUILDERS")) : NBUILD;
-    builders = std::max(1, std::min(std::min(builders, (int)NBUILD), nslabs));
+    int builders = getenv("GOTOH_B200_BUILDERS") ? atoi(getenv("GOTOH_B200_BUILDERS")) : 2;
+    builders = std::max(1, std::min(std::min(builders, (int)NBUILD), std::min(nslabs, nws)));
     std::vector<int> rcs((size_t)builders, 0);
     std::vector<std::string> msgs((size_t)builders);
     std::atomic<int> failed(0);
@@ -987,7 +1009,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
         int mine = 0;
         for (int slab = b; slab < nslabs && !failed.load(); slab += builders, ++mine) {
             // builder b owns workspaces b, b+builders, ...; its previous slab on that workspace must have drained
-            const int per = NWS / builders;
+            const int per = nws / builders;
             gotoh_b200_plan* pl = &plans[b + builders * (mine % per)];
             int rc = GOTOH_B200_OK;
             const double t_a = now_ms();
@@ -1031,7 +1053,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     int rc = GOTOH_B200_OK;
     for (int b = 0; b < builders; ++b)
         if (rcs[(size_t)b] && !rc) rc = fail(rcs[(size_t)b], "%s", msgs[(size_t)b].c_str());
-    for (int w = 0; w < NWS; ++w) {
+    for (int w = 0; w < nws; ++w) {
         const cudaError_t e = cudaStreamSynchronize(ctx->ws[w].stream);
         if (e != cudaSuccess && !rc) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
     }

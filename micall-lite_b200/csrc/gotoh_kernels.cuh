@@ -82,6 +82,7 @@ struct FwdParams {
     int32_t gip, gep;
     int32_t rebase_mask;        // Vec16: R-1 (R power of two); Vec32: unused
     int32_t smin_m1;            // lower bound of any true score, minus 1 (last-column tracking seed)
+    int32_t zshift;             // Vec16: constant (multiple of 4) added to every stored value so that none is negative
     uint32_t four;              // always 4; passed at run time so that acc*four+x compiles to IMAD
     uint4* dir;                 // direction arena
     int2* bnd;                  // Vec32 multi-strip boundary columns: [task_slot][2][bnd_stride]
@@ -106,6 +107,8 @@ struct Vec32 {
     static __device__ __forceinline__ T addmax(T a, T b, T c) { return __viaddmax_s32(a, b, c); }
     static __device__ __forceinline__ T max3(T a, T b, T c) { return __vimax3_s32(a, b, c); }
     static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    static __device__ __forceinline__ T addlin(T a, unsigned, T e) { return a + e; }
+    static __device__ __forceinline__ unsigned lin(int lo, int) { return (unsigned)lo; }
     static __device__ __forceinline__ T clr(T c) { return c & ~3; }
     static __device__ __forceinline__ T both(int x) { return x; }
     static __device__ __forceinline__ T pack(int lo, int) { return lo; }
@@ -122,6 +125,11 @@ struct Vec16 {
     static __device__ __forceinline__ T addmax(T a, T b, T c) { return __viaddmax_s16x2(a, b, c); }
     static __device__ __forceinline__ T max3(T a, T b, T c) { return __vimax3_s16x2(a, b, c); }
     static __device__ __forceinline__ T add(T a, T b) { return __vadd2(a, b); }
+    // a + e per half as ONE 32-bit multiply-add on the FMA pipe: valid because the stored frame is shifted so that the
+    // low halves of a and of a + e are never negative (packed == lo + 65536*hi then, and such "linear" words add
+    // component-wise); e is stored linear (lin), `one` is a run-time 1 so that ptxas keeps the IMAD.
+    static __device__ __forceinline__ T addlin(T a, unsigned one, T e) { return a * one + e; }
+    static __device__ __forceinline__ unsigned lin(int lo, int hi) { return (unsigned)lo + ((unsigned)hi << 16); }
     static __device__ __forceinline__ T clr(T c) { return c & 0xfffcfffcu; }
     static __device__ __forceinline__ T pack(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
     static __device__ __forceinline__ T both(int x) { return pack(x, x); }
@@ -216,9 +224,9 @@ struct Wave {
     enum { K4 = (K + 3) / 4, STEPS = V::STEPS, NP = V::NPAIR, MULTI = (MODE != 0), CTA = (MODE == 2), FLOW = (MODE == 3), XR = 256 };
 
     // ---- per-task / per-strip constants --------------------------------------------------
-    int lane, M, Na, Nb, j0, strip, gep, g4, rebase_mask, smin_m1;
+    int lane, M, Na, Nb, j0, strip, gep, g4, rebase_mask, smin_m1, z4;
     bool last_strip;
-    unsigned four;                 // == 4 at run time; opaque to ptxas so acc*four+x stays an IMAD (FMA pipe)
+    unsigned four, one;                 // == 4 at run time; opaque to ptxas so acc*four+x stays an IMAD (FMA pipe)
     const uint4* prof_lane;        // prof + lane
     const uint8_t* cls;            // cls[i-1] = class of reference row i
     int2* ring;
@@ -261,13 +269,16 @@ struct Wave {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int ja = min(j0 + k + 1, Na), jb = min(j0 + k + 1, Nb);
-            S[k] = V::pack(ja * g4, jb * g4);
-            P[k] = V::pack(ja * g4 + 1, jb * g4 + 1);
+            S[k] = V::pack(ja * g4 + z4, jb * g4 + z4);
+            P[k] = V::pack(ja * g4 + 1 + z4, jb * g4 + 1 + z4);
         }
-        Sd_in = V::pack(min(j0, Na) * g4, min(j0, Nb) * g4);   // S^(0, j0)
-        diag0 = V::both(0);                                     // 4*(i-1)*g at i = 1 (stays 0 outside lane 0)
+        Sd_in = V::pack(min(j0, Na) * g4 + z4, min(j0, Nb) * g4 + z4);   // S^(0, j0)
+        diag0 = lane == 0 ? V::both(z4) : V::both(0);           // 4*(i-1)*g at i = 1 (stays 0 outside lane 0)
         // seed below any reachable score, expressed in the row-0 frame of column N
-        best = V::pack(4 * smin_m1 + Na * g4, 4 * smin_m1 + Nb * g4);
+        // (Vec16: every stored value of an admitted pair is >= 0 after the shift, so -4 is below all of them and, unlike
+        // the plan-wide bound smin_m1, always fits 16 bits)
+        if (NP == 2) best = V::pack(Na * g4 - 4, Nb * g4 - 4);
+        else best = V::pack(4 * smin_m1 + Na * g4, 4 * smin_m1 + Nb * g4);
         best_i_a = best_i_b = 0;
     }
 
@@ -345,7 +356,7 @@ struct Wave {
                 if (k < K) {
                     q = V::addmax(sleft, Uq[k], q);            // Q^ (gotoh.cpp:305-308)
                     const T pp = V::addmax(S[k], c_up, P[k]);  // P^ (gotoh.cpp:311-314)
-                    const T d = V::add(sdiag, (T)ev[kk]);      // D^ (gotoh.cpp:319)
+                    const T d = V::addlin(sdiag, one, (T)ev[kk]);   // D^ (gotoh.cpp:319)
                     const T C = V::max3(d, pp, q);             // select + tie-break (gotoh.cpp:362-395)
                     sdiag = S[k];
                     P[k] = pp;
@@ -404,10 +415,10 @@ struct Wave {
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const int j = j0 + k + 1;
-                    const int sa = (V::lo(S[k]) >> 2) - (roff + j) * gep;
+                    const int sa = ((V::lo(S[k]) - z4) >> 2) - (roff + j) * gep;
                     if (j <= Na && sa >= lr_best_a) { lr_best_a = sa; lr_j_a = j; }
                     if (NP == 2) {
-                        const int sb = (V::hi(S[k]) >> 2) - (roff + j) * gep;
+                        const int sb = ((V::hi(S[k]) - z4) >> 2) - (roff + j) * gep;
                         if (j <= Nb && sb >= lr_best_b) { lr_best_b = sb; lr_j_b = j; }
                     }
                 }
@@ -482,12 +493,14 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
     w.rebase_mask = p.rebase_mask;
     w.smin_m1 = p.smin_m1;
     w.four = p.four;
+    w.one = p.four >> 2;
+    w.z4 = (NP == 2) ? p.zshift : 0;
     w.prof_lane = prof + lane;
     w.ring = reinterpret_cast<int2*>(my_smem + (size_t)p.ncls * K4 * 32 * 16);  // [2][32]
     const int u4 = -4 * p.gip;
     w.c_up = V::both(u4 + 1);          // P^ = max(S^up + 4u+1, P^up)
-    w.c_sl0 = V::both(u4);             // column 0 seen by the Q recurrence: s~ = u   (gotoh.cpp:291)
-    w.c_q0 = V::both(2 * u4 + 2);      //                                     q~ = 2u  (gotoh.cpp:293)
+    w.c_sl0 = V::both(u4 + w.z4);          // column 0 seen by the Q recurrence: s~ = u   (gotoh.cpp:291)
+    w.c_q0 = V::both(2 * u4 + 2 + w.z4);   //                                     q~ = 2u  (gotoh.cpp:293)
     w.c_g4 = V::both(w.g4);
     w.c_g4_lane0 = lane == 0 ? w.c_g4 : V::both(0);
     w.keep = (p.four >> 2) - (lane == 0 ? 1u : 0u);   // 0 for lane 0, 1 elsewhere; opaque so x*keep stays an IMAD
@@ -562,7 +575,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
                             if (ja < Na) ea = trow[qa[ja]] + (p.has_dollar ? brow[cm_a[k]] : 0);
                             if (NP == 2 && ja < Nb) eb = trow[qb[ja]] + (p.has_dollar ? brow[cm_b[k]] : 0);
                         }
-                        e[kk] = V::raw(V::pack(ea, NP == 2 ? eb : 0));
+                        e[kk] = V::lin(ea, NP == 2 ? eb : 0);
                     }
                     prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
                 }
@@ -609,8 +622,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
             const int roff = (NP == 2) ? (i_fin & p.rebase_mask) : i_fin;   // i_fin - base(i_fin)
             const int la = (Na - 1) / K - (nstrips - 1) * 32;   // owner lane within the last strip
             const int lb = (Nb - 1) / K;
-            int best_a = (V::lo(w.best) >> 2) - (roff + Na) * p.gep;
-            int best_b = (V::hi(w.best) >> 2) - (roff + Nb) * p.gep;
+            int best_a = ((V::lo(w.best) - w.z4) >> 2) - (roff + Na) * p.gep;
+            int best_b = ((V::hi(w.best) - w.z4) >> 2) - (roff + Nb) * p.gep;
             best_a = __shfl_sync(0xffffffffu, best_a, la);
             const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a, la);
             best_b = __shfl_sync(0xffffffffu, best_b, lb & 31);
@@ -647,6 +660,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_flow
     w.rebase_mask = p.rebase_mask;
     w.smin_m1 = p.smin_m1;
     w.four = p.four;
+    w.one = p.four >> 2;
+    w.z4 = 0;
     w.prof_lane = prof + lane;
     w.ring = reinterpret_cast<int2*>(my_smem + (size_t)p.ncls * K4 * 32 * 16);
     const int u4 = -4 * p.gip;
@@ -788,6 +803,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_cta(
     w.rebase_mask = p.rebase_mask;
     w.smin_m1 = p.smin_m1;
     w.four = p.four;
+    w.one = p.four >> 2;
+    w.z4 = 0;
     w.prof_lane = prof + lane;
     w.ring = nullptr;
     w.bnd_in = nullptr;

@@ -75,6 +75,38 @@ def test_emu_stop_codon_bonus_rule(emu_aligner, oracle_port, forced_path):
     assert emu_aligner.align_it_aa("KF$$$R", "KFTAGR", 40, 10, 1) == oracle_port.align_it_aa("KF$$$R", "KFTAGR", 40, 10, 1)
 
 
+def test_emu_mixed_int16x2_and_int32_launches_share_a_plan(emu_aligner, oracle_port):
+    """Large penalties and a -20 score ('.') push the longer pairs of a batch past the int16 range proof while
+    the shorter ones stay in int16x2: both kernels then run in ONE plan, the shifted int16 frame
+    must not leak into the int32 launches, and the plan-wide shift must suit every admitted pair."""
+    rng = random.Random(2026)
+    alpha = "ACGTNRYKMSWBDHVacgtnXx*.-Uu"
+    refs, qs = [], []
+    for _ in range(260):
+        a = "".join(rng.choice(alpha if rng.random() < 0.3 else "ACGT") for _ in range(rng.randint(1, 300)))
+        if rng.random() < 0.6:
+            lo = rng.randrange(len(a))
+            b = list(a[lo:lo + rng.randint(1, 300)])
+            for _ in range(rng.randint(0, 5)):
+                b[rng.randrange(len(b))] = rng.choice(alpha)
+            b = "".join(b)
+        else:
+            b = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 300)))
+        refs.append(a)
+        qs.append(b)
+    for gip, gep, term in [(40, 10, 1), (25, 12, 0)]:
+        got = emu_aligner.align_batch(refs, qs, gip, gep, term, 0)
+        for k in range(len(refs)):
+            assert got[k] == oracle_port.align_it(refs[k], qs[k], gip, gep, term), (refs[k], qs[k], gip, gep, term)
+    # the batch really is mixed: a plan over the same pairs reports both paths
+    from gotoh_b200 import packing
+    rb, ro = packing.pack(refs)
+    qb, qo = packing.pack(qs)
+    plan = emu_aligner.plan(rb, ro, None, qb, qo, 40, 10, 1, 0)
+    assert plan.stat(5) > 0 and plan.stat(6) > 0, (plan.stat(5), plan.stat(6))
+    plan.close()
+
+
 def test_emu_many_reference_byte_classes(emu_aligner, oracle_port):
     """A reference using ~120 distinct bytes needs a 120-class query profile: the launcher drops to
     fewer warps per CTA instead of failing."""

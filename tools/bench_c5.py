@@ -1,0 +1,164 @@
+#!/usr/bin/env python
+"""C5: a 10M-pair synthetic MiSeq run = 80 % C2-style reads (align_it 10/3/1 vs the HXB2 pol seed) and
+20 % C3-style amino-acid windows (align_it_aa 40/10/1 vs PR/RT/INT), interleaved by a seeded shuffle and sharded
+statically over the ranks (no collective on the data path; rank r takes every world-th pair of each batch).
+
+    python tools/bench_c5.py [--pairs 10000000] [--batch 1000000]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_c5.py
+
+The run is end to end through gotoh_b200_align_batch with HOST buffers (packing, H2D, kernels, D2H inside the timed
+region); the host keeps one batch of outputs (6.6 GB at 1 M pairs) and reuses it.  One 1M-pair batch is generated
+(20 s of numpy) and batch b uses a seeded permutation of it, so the 10 M pairs are 10 differently ordered passes over
+the same 1 M distinct pairs.  A sample of every rank's last batch is compared with the oracle.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "micall-lite_b200")):
+    sys.path.insert(0, p)
+import numpy as np  # noqa: E402
+
+
+def take(qb, qo, idx):
+    """Sub-batch of packed sequences in the order idx."""
+    lens = (qo[1:] - qo[:-1])[idx]
+    off = np.zeros(len(idx) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    out = np.empty(int(off[-1]), np.uint8)
+    # gather by a flat index: start of each row repeated + position inside the row
+    starts = np.repeat(qo[:-1][idx] - off[:-1], lens)
+    out[:] = qb[starts + np.arange(int(off[-1]))]
+    return out, off
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=10000000)
+    ap.add_argument("--batch", type=int, default=1000000)
+    ap.add_argument("--verify", type=int, default=40)
+    ap.add_argument("--emu", action="store_true", help="self-test of this script in a GPU-less container: kernels under tests/simt_emu")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    import gotoh_b200
+    from gotoh_b200 import packing, workloads
+    from gotoh_b200.api import Aligner, PinnedArray
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("GOTOH_B200_HOST_THREADS", str(max(2, (os.cpu_count() or 8) // world)))
+    if a.emu:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "simt_emu"))
+        import build_emu
+        from gotoh_b200 import _ffi
+        al = Aligner(_ffi.Library(build_emu.build()))
+    else:
+        al = Aligner()
+    nb = a.batch
+    n2, n3 = int(nb * 0.8), nb - int(nb * 0.8)
+    # the seeded shuffle decides which positions of a batch hold reads and which hold amino-acid windows; this rank's
+    # shard is every world-th position
+    rng = np.random.default_rng(20260105)
+    is_aa = np.zeros(nb, bool)
+    is_aa[rng.permutation(nb)[:n3]] = True
+    ref, qb2, qo2 = workloads.c2_reads_packed(n2, seed=20260105)
+    refs3, ridx3, qb3, qo3 = workloads.c3_queries_packed(n3, seed=20260106)
+    rb2, ro2 = packing.pack([ref])
+    rb3, ro3 = packing.pack(refs3)
+    mine2 = np.nonzero(~is_aa)[0]
+    mine2 = np.nonzero(mine2 % world == rank)[0]          # indices into the batch's read list
+    mine3 = np.nonzero(is_aa)[0]
+    mine3 = np.nonzero(mine3 % world == rank)[0]
+    nbatches = (a.pairs + nb - 1) // nb
+    # host buffers of one batch (pinned), reused by every batch
+    lens2 = (qo2[1:] - qo2[:-1])[mine2]
+    cap2 = int((lens2 + len(ref)).sum())
+    lens3 = (qo3[1:] - qo3[:-1])[mine3]
+    mlen3 = np.array([len(r) for r in refs3])[ridx3[mine3]]
+    cap3 = int((lens3 + mlen3).sum())
+    pins = [PinnedArray(al, (int(lens2.sum()),), np.uint8), PinnedArray(al, (cap2,), np.uint8), PinnedArray(al, (cap2,), np.uint8),
+            PinnedArray(al, (len(mine2),), np.int32), PinnedArray(al, (len(mine2),), np.int32),
+            PinnedArray(al, (int(lens3.sum()),), np.uint8), PinnedArray(al, (cap3,), np.uint8), PinnedArray(al, (cap3,), np.uint8),
+            PinnedArray(al, (len(mine3),), np.int32), PinnedArray(al, (len(mine3),), np.int32)]
+    # batch b = a seeded permutation of this rank's shard (prepared outside the timed region)
+    batches = []
+    for b in range(min(nbatches, 3)):                      # three distinct orders, cycled
+        r = np.random.default_rng(1000 + b)
+        p2, p3 = r.permutation(len(mine2)), r.permutation(len(mine3))
+        q2b, q2o = take(qb2, qo2, mine2[p2])
+        q3b, q3o = take(qb3, qo3, mine3[p3])
+        batches.append((q2b, q2o, np.zeros(len(p2), np.int32), q3b, q3o, np.ascontiguousarray(ridx3[mine3[p3]])))
+    cells_batch = float(lens2.sum()) * len(ref) + float((lens3 * mlen3).sum())
+
+    def run_batch(bt):
+        q2b, q2o, r2, q3b, q3o, r3 = bt
+        pins[0].array[:] = q2b                           # the caller's reads arrive in host memory
+        pins[5].array[:] = q3b
+        oo2 = packing.out_offsets(ro2, r2, q2o)
+        oo3 = packing.out_offsets(ro3, r3, q3o)
+        al.align_packed(rb2, ro2, r2, pins[0].array, q2o, 10, 3, 1, gotoh_b200.NT, out_off=oo2,
+                        out=(pins[1].array, pins[2].array, pins[3].array, pins[4].array), device_mask=1 << local)
+        al.align_packed(rb3, ro3, r3, pins[5].array, q3o, 40, 10, 1, gotoh_b200.HIV25, out_off=oo3,
+                        out=(pins[6].array, pins[7].array, pins[8].array, pins[9].array), device_mask=1 << local)
+        return oo2, oo3
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    run_batch(batches[0])                                 # warm-up: workspaces, pinned staging
+    barrier()
+    t0 = time.perf_counter()
+    for b in range(nbatches):
+        oo2, oo3 = run_batch(batches[b % len(batches)])
+    barrier()
+    dt = time.perf_counter() - t0
+    # verify a sample of the last batch against the oracle
+    from oracle.oracle import Oracle, have_reference
+    ora = Oracle("reference" if have_reference() else "port")
+    bt = batches[(nbatches - 1) % len(batches)]
+    bad = 0
+    a2 = packing.unpack(pins[1].array, oo2, pins[3].array)
+    b2 = packing.unpack(pins[2].array, oo2, pins[3].array)
+    for k in range(0, len(bt[2]), max(1, len(bt[2]) // a.verify)):
+        q = bt[0][bt[1][k]:bt[1][k + 1]].tobytes().decode()
+        bad += (a2[k], b2[k], int(pins[4].array[k])) != ora.align_it(ref, q, 10, 3, 1)
+    a3 = packing.unpack(pins[6].array, oo3, pins[8].array)
+    b3 = packing.unpack(pins[7].array, oo3, pins[8].array)
+    for k in range(0, len(bt[5]), max(1, len(bt[5]) // a.verify)):
+        q = bt[3][bt[4][k]:bt[4][k + 1]].tobytes().decode()
+        bad += (a3[k], b3[k], int(pins[9].array[k])) != ora.align_it_aa(refs3[int(bt[5][k])], q, 40, 10, 1)
+    if dist is not None:
+        import torch
+        t = torch.tensor([dt, float(bad)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, bad = float(t[0]), int(t[1])
+        c = torch.tensor([cells_batch], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        cells_all = float(c[0]) * nbatches
+    else:
+        cells_all = cells_batch * nbatches
+    if rank == 0:
+        print(json.dumps({"config": "C5 10M-pair MiSeq mix (80% C2 reads, 20% C3 aa windows), strong scaling, end to end with host buffers",
+                          "pairs": nbatches * nb, "n_gpus": world, "seconds": dt, "alignments_per_s": nbatches * nb / dt,
+                          "gcups_e2e": cells_all / dt / 1e9, "cells": cells_all, "scaling": "strong",
+                          "verified_per_rank": 2 * a.verify, "mismatches": bad}), flush=True)
+    for p_ in pins:
+        p_.free()
+    if dist is not None:
+        dist.destroy_process_group()
+    if bad:
+        raise SystemExit("C5: %d sampled pairs differ from the oracle" % bad)
+
+
+if __name__ == "__main__":
+    main()
