@@ -853,7 +853,9 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
                                   FwdSmem<Vec32, 8>::per_warp(pl->ncls) * FWD_WARPS <= 200 * 1024;
                 if (flow) {
                     // K2 default: strip dataflow - every (pair, strip) is a warp task, any number of pairs fills the GPU
-                    CU(cudaMemsetAsync(ws->d_flow.p, 0, (size_t)L.nslots * sizeof(int32_t), ws->stream));
+                    // boundary columns and last-row partials are self-validating (see Wave::nextb): preset them to "empty"
+                    CU(cudaMemsetAsync(ws->d_bnd.p, 0xff, (size_t)L.nslots * (size_t)pl->bnd_stride * sizeof(int2), ws->stream));
+                    CU(cudaMemsetAsync(ws->d_flow.p + pl->flow_slots, 0x80, (size_t)L.nslots * sizeof(int32_t), ws->stream));
                     fp.tasks = ws->d_stasks.p; fp.task_first = L.stask_first; fp.task_count = L.nslots;
                     fp.prog = ws->d_flow.p; fp.part_best = ws->d_flow.p + pl->flow_slots; fp.part_j = ws->d_flow.p + 2 * (size_t)pl->flow_slots;
                     rc = launch_forward_flow(pl, fp, L.nslots);

@@ -65,6 +65,7 @@ def main():
     ap.add_argument("--c4", type=int, default=2000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--verify", type=int, default=100)
+    ap.add_argument("--c4-modes", default="flow,cta,warp", help="long-pair kernels to time on C4 (GOTOH_B200_LONG values)")
     a = ap.parse_args()
     import gotoh_b200
     from gotoh_b200 import packing, workloads
@@ -84,7 +85,7 @@ def main():
     if a.c4:
         refs, ridx, qb, qo = workloads.c4_pairs_packed(a.c4)
         rb, ro = packing.pack(refs)
-        for mode in ("flow", "cta", "warp"):
+        for mode in a.c4_modes.split(","):
             os.environ["GOTOH_B200_LONG"] = mode
             run("C4 align_it(15,3,1) HCV genomes, long-pair kernel=%s" % mode, al, ora, gotoh_b200.NT, rb, ro, ridx, qb, qo,
                 15, 3, 1, max(1, a.steps - 1), min(a.verify, 6))
