@@ -29,7 +29,7 @@
 namespace gotoh {
 namespace g2f {
 
-enum { INF = 1 << 29, BIGE = 1 << 28, FSTEPS = 4, PUB = 32 };
+enum { INF = 1 << 29, BIGE = 1 << 28, FSTEPS = 4, PUB = 32, BND_EMPTY = (int)0x80808080, PART_EMPTY2 = (int)0x80808080 };
 
 struct StripTask {
     int32_t pair;
@@ -91,6 +91,7 @@ struct Fwd {
     int2* ring;
     const int2* bnd_in;
     int2* bnd_out;
+    int2 nextb;                    // MULTI: the next window of the left boundary column, prefetched
     int vq[K];
     int R[K], P[K], nRu[K];
     int sendR, sendQ, Rd_in, next_cls;
@@ -122,10 +123,20 @@ struct Fwd {
         int rdiag = Rd_in;
         if (MULTI && strip > 0) {
             if (((t - 1) & 31) == 0) {
+                // self-validating boundary column (host preset: 0x80 bytes, BND_EMPTY is no reachable cost): re-read a row
+                // until the left strip has written it, and prefetch the next window a window ahead
                 __syncwarp();
                 const int row = t + lane;
-                int2 b = make_int2(0, 0);
-                if (row >= 1 && row <= M) b = ld_cg(&bnd_in[row]);
+                const bool real_row = (row >= 1 && row <= M);
+                int2 b = nextb;
+                for (;;) {
+                    const bool miss = real_row && b.x == BND_EMPTY;
+                    if (!__any_sync(0xffffffffu, miss)) break;
+                    if (miss) b = ld_cg(&bnd_in[row]);
+                    gotoh_pause();
+                }
+                const int row2 = row + 32;
+                nextb = (row2 >= 1 && row2 <= M) ? ld_cg(&bnd_in[row2]) : make_int2(0, 0);
                 ring[(((t - 1) >> 5) & 1) * 32 + lane] = b;
                 __syncwarp();
             }
@@ -274,20 +285,11 @@ __global__ void __launch_bounds__(128, 4) k2f(const Params p) {
         w.row0_init(p.is_global);
         w.next_cls = w.cls[-lane];
 
-        int32_t* prog_in = p.prog_f + ex.slot0 + strip - 1;
-        int32_t* prog_out = p.prog_f + ex.slot0 + strip;
+        w.nextb = make_int2(BND_EMPTY, BND_EMPTY);
         uint4* dlo = BITS ? p.lo + pr.dir_off + (int64_t)strip * nblk * 32 + lane : nullptr;
         uint4* dhi = BITS ? p.hi + pr.dir_off + (int64_t)strip * nblk * 32 + lane : nullptr;
         for (int tb = 0; tb < nblk; ++tb) {
             const int t0 = tb * FSTEPS + 1, hi = t0 + FSTEPS - 1;
-            if (MULTI && strip > 0 && ((t0 - 1) & 31) == 0) {
-                // lane 0 consumes rows t0 .. t0+31 of the left strip's last column during the next 32 steps
-                if (lane == 0) {
-                    const int need = min(t0 + 31, M);
-                    while (ld_volatile(prog_in) < need) gotoh_pause();
-                }
-                __syncwarp();
-            }
             const bool slow = (t0 <= 31) || (hi >= M);
             if (slow) {
 #pragma unroll
@@ -297,10 +299,6 @@ __global__ void __launch_bounds__(128, 4) k2f(const Params p) {
                 for (int s = 0; s < FSTEPS; ++s) w.template step<false>(t0 + s, s, p.is_global);
             }
             if (BITS) { dlo[(int64_t)tb * 32] = w.wlo; dhi[(int64_t)tb * 32] = w.whi; }
-            if (MULTI && !w.last_strip && ((hi & (PUB - 1)) == 0) && hi - 31 >= 1 && hi - 31 < M) {
-                __syncwarp();
-                if (lane == 31) { __threadfence(); st_volatile(prog_out, hi - 31); }
-            }
         }
 
         // ---- bottom-row partial of this strip (smallest j wins ties), then the final publish ------------
@@ -312,9 +310,8 @@ __global__ void __launch_bounds__(128, 4) k2f(const Params p) {
             if (om < row_min || (om == row_min && oj < row_j)) { row_min = om; row_j = oj; }
         }
         if (MULTI && !w.last_strip) {
-            if (lane == 0) { p.part_min[ex.slot0 + strip] = row_min; p.part_j[ex.slot0 + strip] = row_j; }
-            __syncwarp();
-            if (lane == 31) { __threadfence(); st_volatile(prog_out, M); }
+            // partial of this strip: column first, then (fenced) the minimum, which the host preset to PART_EMPTY2
+            if (lane == 0) { p.part_j[ex.slot0 + strip] = row_j; __threadfence(); st_volatile(&p.part_min[ex.slot0 + strip], row_min); }
             continue;
         }
         // ---- last strip: start cell (_gotoh2.c:327-352) ---------------------------------------------------
@@ -331,7 +328,10 @@ __global__ void __launch_bounds__(128, 4) k2f(const Params p) {
                 int rm = 0, rj = 0;                          // R(l1, 0) = 0 in local mode (_gotoh2.c:111)
                 if (MULTI) {
                     for (int s = 0; s < nstrips - 1; ++s) {
-                        const int pm = ld_cg(&p.part_min[ex.slot0 + s]), pj = ld_cg(&p.part_j[ex.slot0 + s]);
+                        int pm;                                   // the strip may still be writing its partial
+                        while ((pm = ld_volatile(&p.part_min[ex.slot0 + s])) == PART_EMPTY2) gotoh_pause();
+                        __threadfence();
+                        const int pj = ld_cg(&p.part_j[ex.slot0 + s]);
                         if (pm < rm) { rm = pm; rj = pj; }
                     }
                 }
@@ -715,8 +715,7 @@ __global__ void __launch_bounds__(128, 8) k2r(const Params p) {
         r.finA_dn = 0; r.finC_dn = 0; r.DE_dn = 0; r.send = 0; r.in_c_prev = 0;
         r.rb_out = p.rbnd + ex.bnd_off + (int64_t)(strip - 1) * (M + 2);                // read by strip-1
         const uint8_t* rb_in = p.rbnd + ex.bnd_off + (int64_t)strip * (M + 2);          // written by strip+1
-        int32_t* prog_in = p.prog_r + ex.slot0 + strip + 1;
-        int32_t* prog_out = p.prog_r + ex.slot0 + strip;
+        unsigned nextrb = 0xffu;                    // nothing prefetched yet
         uint8_t* ring = &s_ring[warp][0][0];
 
         const uint4* slo = p.lo + pr.dir_off + (int64_t)strip * nblk * 32 + lane;
@@ -727,19 +726,23 @@ __global__ void __launch_bounds__(128, 8) k2r(const Params p) {
             const int t0 = tb * FSTEPS + 1, thi = t0 + FSTEPS - 1;
             if (MULTI && !last_strip && ((thi & 31) == 0 || tb == nblk - 1)) {
                 // lane 31 consumes the right strip's first column: window wdw covers steps 32*wdw+1 .. 32*wdw+32,
-                // i.e. lane-31 rows 32*wdw-30 .. 32*wdw+1; all of them must have been published (counts down)
+                // i.e. lane-31 rows 32*wdw-30 .. 32*wdw+1.  The column is self-validating (host preset 0xff, real bytes
+                // are < 16): re-read a row until the right strip has written it; the next (lower) window is prefetched.
                 const int wdw = (thi - 1) >> 5;
-                const int lowrow = 32 * wdw - 30;
-                if (lane == 0) {
-                    const int need = max(lowrow, 1);
-                    while (ld_volatile(prog_in) > need) gotoh_pause();
-                    __threadfence();
+                const int row = 32 * wdw - 30 + lane;
+                const bool real_row = (row >= 1 && row <= M);
+                unsigned b = nextrb;
+                for (;;) {
+                    const bool miss = real_row && b == 0xffu;
+                    if (!__any_sync(0xffffffffu, miss)) break;
+                    if (miss) b = ld_cg(&rb_in[row]);
+                    gotoh_pause();
                 }
+                if (!real_row) b = 0;
+                const int row2 = row - 32;
+                nextrb = (row2 >= 1 && row2 <= M) ? (unsigned)ld_cg(&rb_in[row2]) : 0xffu;
                 __syncwarp();
-                const int row = lowrow + lane;
-                uint8_t b = 0;
-                if (row >= 1 && row <= M) b = ld_cg(&rb_in[row]);
-                ring[(wdw & 1) * 32 + lane] = b;
+                ring[(wdw & 1) * 32 + lane] = (uint8_t)b;
                 __syncwarp();
             }
             const uint4 l4 = nl4;
@@ -758,15 +761,6 @@ __global__ void __launch_bounds__(128, 8) k2r(const Params p) {
                 h4.x = r.template step<true>(t0 + 0, l4.x, h4.x);
             }
             shi[(int64_t)tb * 32] = h4;
-            if (MULTI && strip > 0 && ((t0 - 1) & (PUB - 1)) == 0 && t0 > 1 && t0 <= M) {
-                // lane 0 has finished rows >= t0
-                __syncwarp();
-                if (lane == 0) { __threadfence(); st_volatile(prog_out, t0); }
-            }
-        }
-        if (MULTI && strip > 0) {
-            __syncwarp();
-            if (lane == 0) { __threadfence(); st_volatile(prog_out, 0); }
         }
     }
 }

@@ -320,8 +320,12 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
             groups.push_back(g);
         }
         CU(cudaMemcpy(b.tasks.p, tasks.data(), tasks.size() * sizeof(StripTask), cudaMemcpyHostToDevice));
-        CU(cudaMemset(b.prog.p, 0, (size_t)ch.slots * sizeof(int32_t)));                       // forward: rows published
-        CU(cudaMemset(b.prog.p + slots_max, 0x7f, ((size_t)ch.slots + 2) * sizeof(int32_t)));  // reverse: lowest row done
+        // strip boundaries and last-row partials are self-validating: preset them to "empty" (BND_EMPTY, 0xff, PART_EMPTY2)
+        if (ch.bnd > 0) {
+            CU(cudaMemset(b.fbnd.p, 0x80, (size_t)ch.bnd * sizeof(int2)));
+            CU(cudaMemset(b.rbnd.p, 0xff, (size_t)ch.bnd));
+        }
+        CU(cudaMemset(b.part.p, 0x80, (size_t)ch.slots * sizeof(int32_t)));
         CU(cudaMemset(b.counters.p, 0, 24 * sizeof(uint32_t)));
         Params p;
         memset(&p, 0, sizeof(p));

@@ -179,6 +179,7 @@ struct Launch {
     int task_first, task_count;
     int rebase_mask;
     int multi_strip;
+    int hw = 0;            // Vec16 on half-warp wavefronts: tasks are taken in twos
     int nslots = 0;        // multi-strip launches: (pair, strip) slots = strip tasks of the dataflow kernel
     int stask_first = 0;   // first strip task in d_stasks
 };
@@ -231,6 +232,16 @@ int pick_K(int n) {
     for (int k : kSupportedK) if (32 * k >= n) return k;
     return kMaxK;
 }
+// Queries of at most 128 columns run as two 16-lane wavefronts per warp (k_forward<..., HALF>): K columns per lane with
+// 16*K >= n.  GOTOH_B200_HALF=0 pins the 32-lane kernels (tests, A/B measurements; still a GPU path).
+thread_local bool t_half_off = false;    // read from the environment once per plan_build
+bool half_ok(int n) { return !t_half_off && n <= 16 * kMaxK; }
+int pick_K_half(int n) {
+    for (int k : kSupportedK) if (16 * k >= n) return k;
+    return kMaxK;
+}
+// kernel selector of an int16x2 pair: K, plus 16 when it runs on half-warp wavefronts
+int pick_KH(int n) { return half_ok(n) ? (16 | pick_K_half(n)) : pick_K(n); }
 
 // "range proof" for the int16x2 path: with rebase period R every value the Vec16 kernel
 // forms for real cells stays inside int16.  All quantities in stored units.
@@ -296,7 +307,7 @@ int host_threads(int64_t bytes) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(hw, bytes >> 20));
 }
 
-template <class V, int K, bool MULTI>
+template <class V, int K, bool MULTI, bool HALF = false>
 int launch_forward_k(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
     const Workspace* ws = pl->ws;
     const size_t per_warp = FwdSmem<V, K>::per_warp(pl->ncls);
@@ -305,7 +316,7 @@ int launch_forward_k(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
     const size_t smem = per_warp * warps;
     if (smem > 220 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
-    CU(cudaFuncSetAttribute(k_forward<V, K, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute((k_forward<V, K, MULTI, HALF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid: enough CTAs to fill every SM, tasks are pulled from a counter
     int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(GOTOH_MIN_CTAS, (200 * 1024) / std::max<size_t>(smem, 1)));
     int grid = std::min((ntasks + warps - 1) / warps, ws->sm_count * ctas_per_sm);
@@ -314,7 +325,7 @@ int launch_forward_k(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
     if (fp.task_limit > 0 && !MULTI) grid = (ntasks + warps * fp.task_limit - 1) / (warps * fp.task_limit);
     if (MULTI) grid = std::min<long long>(grid, (long long)ws->d_bnd.cap / (2 * pl->bnd_stride * warps));
     grid = std::max(grid, 1);
-    GOTOH_LAUNCH((k_forward<V, K, MULTI>), dim3(grid), dim3(warps * 32), smem, ws->stream, fp);
+    GOTOH_LAUNCH((k_forward<V, K, MULTI, HALF>), dim3(grid), dim3(warps * 32), smem, ws->stream, fp);
     CU(cudaGetLastError());
     return GOTOH_B200_OK;
 }
@@ -355,6 +366,19 @@ int launch_forward(const gotoh_b200_plan* pl, const FwdParams& fp, int K, int nt
         case 4: return launch_forward_k<V, 4, MULTI>(pl, fp, ntasks);
         case 6: return launch_forward_k<V, 6, MULTI>(pl, fp, ntasks);
         case 8: return launch_forward_k<V, 8, MULTI>(pl, fp, ntasks);
+    }
+    return fail(GOTOH_B200_EINVAL, "unsupported K=%d", K);
+}
+
+int launch_forward_half(const gotoh_b200_plan* pl, const FwdParams& fp, int K, int nwarp_tasks) {
+    FwdParams q = fp;
+    q.task_count = nwarp_tasks;          // the kernel counts warps' worth of work: two task entries each
+    switch (K) {
+        case 2: return launch_forward_k<Vec16, 2, false, true>(pl, q, nwarp_tasks);
+        case 3: return launch_forward_k<Vec16, 3, false, true>(pl, q, nwarp_tasks);
+        case 4: return launch_forward_k<Vec16, 4, false, true>(pl, q, nwarp_tasks);
+        case 6: return launch_forward_k<Vec16, 6, false, true>(pl, q, nwarp_tasks);
+        case 8: return launch_forward_k<Vec16, 8, false, true>(pl, q, nwarp_tasks);
     }
     return fail(GOTOH_B200_EINVAL, "unsupported K=%d", K);
 }
@@ -567,6 +591,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     }
     pl->smin_m1 = (int)(smin_all - 2LL * pl->gip - pl->gep - 2);
     const int force = getenv("GOTOH_B200_FORCE_PATH") ? atoi(getenv("GOTOH_B200_FORCE_PATH")) : 0;  // tests: 32
+    t_half_off = getenv("GOTOH_B200_HALF") && atoi(getenv("GOTOH_B200_HALF")) == 0;                  // tests: 32-lane wavefronts only
     std::vector<KeyIdx> elig, wide;
     elig.reserve((size_t)n);
     int worstM = 0, worstN = 0;   // for picking R: fits_int16 is monotone in min(M,N) and K
@@ -588,7 +613,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         ki.idx = (uint32_t)x;
         if (ok) {
             // group by (K, M desc, ref, N desc): partners share the reference and have similar width
-            ki.key = ((uint64_t)K << 59) | ((uint64_t)(0xffffff - h.M) << 35) | ((uint64_t)h.ref << 9) | (uint64_t)(511 - std::min(h.N, 511));
+            ki.key = ((uint64_t)pick_KH(h.N) << 59) | ((uint64_t)(0xffffff - h.M) << 35) | ((uint64_t)h.ref << 9) | (uint64_t)(511 - std::min(h.N, 511));
             elig.push_back(ki);
             if (std::min(h.M, h.N) > std::min(worstM, worstN)) { worstM = h.M; worstN = h.N; }
         } else {
@@ -615,11 +640,11 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     phase(5);
 
     CU(ws->h_pairs.ensure((size_t)n));
-    CU(ws->h_tasks.ensure((size_t)n));
+    CU(ws->h_tasks.ensure((size_t)n * 2 + 2));      // one entry per couple / single, plus at most one filler each (half-warp kernels take entries in twos)
     PairInfo* pairs = ws->h_pairs.p;
     Task* tasks = ws->h_tasks.p;
     size_t n_tasks = 0;
-    struct TaskMeta { int x2, K; int64_t arena; int multi; };
+    struct TaskMeta { int x2, K; int64_t arena; int multi; int hw; int share_prev; int dummy; };   // hw: half-warp wavefronts; share_prev: second couple of a warp (same arena slab); dummy: filler entry, owns no pairs
     std::vector<TaskMeta> tmeta;
     tmeta.reserve((size_t)n);
     int64_t ops_words = 0;
@@ -635,26 +660,47 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         pi.M = h.M; pi.N = h.N;
         pi.K = (int16_t)K; pi.x2 = (int8_t)x2; pi.half = (int8_t)half;
         pi.orig = h.orig;
-        pi.nblk = x2 ? (h.M + 31 + 3) / 4 : (h.M + 31 + 7) / 8;
+        pi.nblk = x2 ? (h.M + ((half & 4) ? 15 : 31) + 3) / 4 : (h.M + 31 + 7) / 8;   // wavefront fill: 31 rows, 15 on half-warp wavefronts
+        pi.half = (int8_t)(half & 3);
         if (ops_words + (h.M + h.N + 15) / 16 > 0x7fffffffLL) return -1;
         pi.ops_off = (int32_t)ops_words;
         ops_words += (h.M + h.N + 15) / 16;
         return next_pair++;
     };
+    int open_quad = -1;            // task index of a half-warp couple that still lacks its warp partner
+    auto close_quad = [&]() {
+        // a warp of the HALF kernel always takes two task entries: fill the gap with a copy of the lone couple (it
+        // recomputes the same pairs on lanes 16-31 and writes identical results)
+        if (open_quad < 0) return;
+        tasks[n_tasks++] = tasks[open_quad];
+        tmeta.push_back({1, tmeta[(size_t)open_quad].K, 0, 0, 1, 1, 1});
+        open_quad = -1;
+    };
     for (size_t x = 0; x < elig.size();) {
         const uint32_t a = elig[x].idx;
-        const int K = pick_K(hp[a].N);
+        const int KH = pick_KH(hp[a].N), K = KH & 15, hw = KH >> 4;
         int64_t b = -1;
-        if (x + 1 < elig.size() && hp[elig[x + 1].idx].ref == hp[a].ref && pick_K(hp[elig[x + 1].idx].N) == K) b = elig[x + 1].idx;
+        if (x + 1 < elig.size() && hp[elig[x + 1].idx].ref == hp[a].ref && pick_KH(hp[elig[x + 1].idx].N) == KH) b = elig[x + 1].idx;
+        // second couple of a warp: same kernel, same reference (same M keeps the block loop warp-uniform)
+        bool second = false;
+        if (hw && open_quad >= 0) {
+            const PairInfo& first = pairs[tasks[open_quad].pair_a];
+            second = tmeta[(size_t)open_quad].K == K && first.ref_pos == ref_pos[(size_t)hp[a].ref] && first.M == hp[a].M;
+            if (!second) close_quad();
+        }
+        if (!hw) close_quad();
+        const int hbits = (hw ? 4 : 0) | (second ? 2 : 0);
         Task t;
-        t.pair_a = add_pair(a, K, 1, 0);
-        t.pair_b = b >= 0 ? add_pair((uint32_t)b, K, 1, 1) : -1;
+        t.pair_a = add_pair(a, K, 1, hbits | 0);
+        t.pair_b = b >= 0 ? add_pair((uint32_t)b, K, 1, hbits | 1) : -1;
         if (t.pair_a < 0 || (b >= 0 && t.pair_b < 0)) return fail(GOTOH_B200_ERANGE, "op-script arena exceeds 2^31 words; split the batch");
         tasks[n_tasks++] = t;
-        tmeta.push_back({1, K, (int64_t)pairs[t.pair_a].nblk * 32, 0});
+        tmeta.push_back({1, K, second ? 0 : (int64_t)pairs[t.pair_a].nblk * 32, 0, hw, second ? 1 : 0, 0});
+        if (hw) open_quad = second ? -1 : (int)n_tasks - 1;
         pl->pairs_x2 += (b >= 0) ? 2 : 1;
         x += (b >= 0) ? 2 : 1;
     }
+    close_quad();
     for (const KeyIdx& ki : wide) {
         const uint32_t a = ki.idx;
         const int K = pick_K(hp[a].N);
@@ -664,7 +710,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         if (t.pair_a < 0) return fail(GOTOH_B200_ERANGE, "op-script arena exceeds 2^31 words; split the batch");
         const int nstrips = (hp[a].N + 32 * K - 1) / (32 * K);
         tasks[n_tasks++] = t;
-        tmeta.push_back({0, K, (int64_t)nstrips * pairs[t.pair_a].nblk * 32, nstrips > 1});
+        tmeta.push_back({0, K, (int64_t)nstrips * pairs[t.pair_a].nblk * 32, nstrips > 1, 0, 0, 0});
         pl->pairs_x1 += 1;
     }
 
@@ -716,13 +762,15 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         used = 0;
     };
     int pair_cursor = 0;
+    int64_t prev_off = 0;
     for (size_t t = 0; t < n_tasks; ++t) {
         const TaskMeta& m = tmeta[t];
-        if (used + m.arena > budget_u4) { flush(); cur.pair_first = pair_cursor; cur.pair_count = 0; }
-        if (cur.launches.empty() || cur.launches.back().x2 != m.x2 || cur.launches.back().K != m.K ||
-            cur.launches.back().multi_strip != m.multi) {
+        // (the second entry of a half-warp warp shares its partner's slab: it never opens a chunk or a launch)
+        if (!m.share_prev && used + m.arena > budget_u4) { flush(); cur.pair_first = pair_cursor; cur.pair_count = 0; }
+        if (!m.share_prev && (cur.launches.empty() || cur.launches.back().x2 != m.x2 || cur.launches.back().K != m.K ||
+                              cur.launches.back().multi_strip != m.multi || cur.launches.back().hw != m.hw)) {
             Launch L; L.x2 = m.x2; L.K = m.K; L.task_first = (int)t; L.task_count = 0;
-            L.rebase_mask = R - 1; L.multi_strip = m.multi;
+            L.rebase_mask = R - 1; L.multi_strip = m.multi; L.hw = m.hw;
             cur.launches.push_back(L);
         }
         cur.launches.back().task_count++;
@@ -733,10 +781,14 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
             pairs[tk.pair_a].pad1 = cur.launches.back().nslots;
             cur.launches.back().nslots += (pp.N + 32 * pp.K - 1) / (32 * pp.K);
         }
-        pairs[tk.pair_a].dir_off = used;
-        if (tk.pair_b >= 0) pairs[tk.pair_b].dir_off = used;
+        if (!m.dummy) {
+            const int64_t at = m.share_prev ? prev_off : used;
+            pairs[tk.pair_a].dir_off = at;
+            if (tk.pair_b >= 0) pairs[tk.pair_b].dir_off = at;
+            prev_off = at;
+        }
         used += m.arena;
-        const int np = tk.pair_b >= 0 ? 2 : 1;
+        const int np = m.dummy ? 0 : (tk.pair_b >= 0 ? 2 : 1);
         cur.pair_count += np;
         pair_cursor += np;
     }
@@ -839,7 +891,8 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
             fp.task_limit = (!timed && !L.multi_strip) ? pl->task_limit : 0;
             // multi-strip tasks only exist with K = 8 (pick_K), and only on the int32 path
             int rc;
-            if (L.x2) rc = launch_forward<Vec16, false>(pl, fp, L.K, L.task_count);
+            if (L.x2 && L.hw) rc = launch_forward_half(pl, fp, L.K, L.task_count / 2);
+            else if (L.x2) rc = launch_forward<Vec16, false>(pl, fp, L.K, L.task_count);
             else if (!L.multi_strip) rc = launch_forward<Vec32, false>(pl, fp, L.K, L.task_count);
             else {
                 // K2: with few long pairs a CTA per pair (4 warps pipelined over adjacent strips) keeps

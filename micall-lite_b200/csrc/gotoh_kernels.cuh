@@ -58,7 +58,7 @@ struct PairInfo {
     int32_t ops_off;   // first uint32 of this pair's op script
     int16_t K;         // query columns per lane
     int8_t x2;         // 1: Vec16 arena (32 dir bits per lane-step, two alignments)
-    int8_t half;       // which half of the Vec16 word belongs to this pair
+    int8_t half;       // bit 0: which half of the Vec16 word belongs to this pair; bit 1: second couple of a HALF-kernel warp (lanes 16-31)
     int32_t orig;      // caller's pair index (relative to the plan's first pair)
     int32_t out_cap;   // caller's output stride for this pair (>= M+N); the tail past out_len is zeroed
     int32_t pad1;
@@ -161,9 +161,10 @@ __device__ __forceinline__ DirAddr dir_addr(const PairInfo& p, int i, int j) {
     const int tt = i + lane - 1;  // step index, 0-based
     DirAddr a;
     if (p.x2) {
+        // half bit 0: which 16-bit half of the word; bit 1 (HALF kernels): this pair's couple ran on lanes 16-31
         const int tb = tt >> 2, s = tt & 3;
-        a.word = ((p.dir_off + ((int64_t)strip * p.nblk + tb) * 32 + lane) << 2) + s;
-        a.shift = 16 * p.half + 2 * (K - 1 - k);
+        a.word = ((p.dir_off + ((int64_t)strip * p.nblk + tb) * 32 + lane + ((p.half & 2) ? 16 : 0)) << 2) + s;
+        a.shift = 16 * (p.half & 1) + 2 * (K - 1 - k);
     } else {
         const int tb = tt >> 3, s = tt & 7;
         a.word = ((p.dir_off + ((int64_t)strip * p.nblk + tb) * 32 + lane) << 2) + (s >> 1);
@@ -188,9 +189,12 @@ __device__ __forceinline__ int stop_mask(const uint8_t* b, int N, int j) {
 
 template <class V, int K>
 struct FwdSmem {
-    enum { K4 = (K + 3) / 4 };
-    // profile: [class][K4][lane] of 4 packed entries; + a 2x32 int2 ring for multi-strip boundaries
-    static __host__ __device__ size_t per_warp(int ncls) { return (size_t)ncls * K4 * 32 * 16 + 2 * 32 * sizeof(int2); }
+    enum { K4 = (K + 3) / 4, USE2 = (K == 2 || K == 6), E2 = (K + 1) / 2, ROW_BYTES = USE2 ? E2 * 8 : K4 * 16 };
+    // profile: [class][K4][lane] of 4 packed entries (K = 2, 6: [class][K/2][lane] of 2 entries - no padding words, so
+    // a 21-class amino-acid profile at K = 6 leaves room for 3 CTAs per SM instead of 2);
+    // + a 2x32 int2 ring for multi-strip boundaries
+    static __host__ __device__ size_t prof_bytes(int ncls) { return (size_t)ncls * ROW_BYTES * 32; }
+    static __host__ __device__ size_t per_warp(int ncls) { return prof_bytes(ncls) + 2 * 32 * sizeof(int2); }
 };
 
 // State of one warp sweeping one strip (32*K query columns) down the reference.
@@ -223,7 +227,7 @@ template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldc
 template <class V, int K, int MODE>
 struct Wave {
     typedef typename V::T T;
-    enum { K4 = (K + 3) / 4, STEPS = V::STEPS, NP = V::NPAIR, MULTI = (MODE != 0), CTA = (MODE == 2), FLOW = (MODE == 3), XR = 256 };
+    enum { K4 = (K + 3) / 4, USE2 = (K == 2 || K == 6), E2 = (K + 1) / 2, STEPS = V::STEPS, NP = V::NPAIR, MULTI = (MODE != 0), CTA = (MODE == 2), FLOW = (MODE == 3), XR = 256 };
 
     // ---- per-task / per-strip constants --------------------------------------------------
     int lane, M, Na, Nb, j0, strip, gep, g4, rebase_mask, smin_m1, z4;
@@ -358,13 +362,24 @@ struct Wave {
         Sd_in = Sl;
 
         // ---- K cells of row i ------------------------------------------------------------------
-        const uint4* prow = prof_lane + my_cls * (K4 * 32);
+        unsigned evs[K4 * 4];
+        if (USE2) {
+            const uint2* prow = reinterpret_cast<const uint2*>(prof_lane) + my_cls * (E2 * 32);
+#pragma unroll
+            for (int kp = 0; kp < E2; ++kp) { const uint2 e2 = prow[kp * 32]; evs[2 * kp] = e2.x; evs[2 * kp + 1] = e2.y; }
+        } else {
+            const uint4* prow = prof_lane + my_cls * (K4 * 32);
+#pragma unroll
+            for (int kq = 0; kq < K4; ++kq) {
+                const uint4 e4 = prow[kq * 32];
+                evs[4 * kq] = e4.x; evs[4 * kq + 1] = e4.y; evs[4 * kq + 2] = e4.z; evs[4 * kq + 3] = e4.w;
+            }
+        }
         T sleft = Sl, q = Ql;
         unsigned accC = 0, accS = 0;
 #pragma unroll
         for (int kq = 0; kq < K4; ++kq) {
-            const uint4 e4 = prow[kq * 32];
-            const unsigned ev[4] = {e4.x, e4.y, e4.z, e4.w};
+            const unsigned* ev = evs + 4 * kq;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const int k = kq * 4 + kk;
@@ -478,13 +493,22 @@ struct Wave {
     }
 };
 
-template <class V, int K, bool MULTI>
+// HALF (Vec16, single strip, queries of at most 16*K columns): the warp carries TWO independent wavefronts of 16 lanes,
+// lanes 0-15 one couple of alignments and lanes 16-31 another couple against the same reference (same M, so the block
+// loop stays warp-uniform).  Short queries (84-aa windows, K = 6) then pay half the wavefront fill/drain (15 rows, not 31)
+// and amortise the per-step overhead over twice the columns per lane.  Tasks come in twos: entry 2*tsk + (lane >> 4).
+// Both couples share one arena slab: physical lane = wave lane + 16 * (second couple), see dir_addr().  The hand-over
+// shuffle needs no width: wave lane 0 of either half overrides what it receives with the column-0 injection.
+template <class V, int K, bool MULTI, bool HALF = false>
 __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(const FwdParams p) {
+    static_assert(!HALF || (V::NPAIR == 2 && !MULTI), "HALF is a single-strip int16x2 mode");
     typedef typename V::T T;
     typedef Wave<V, K, MULTI ? 1 : 0> W;
-    enum { K4 = W::K4, STEPS = V::STEPS, NP = V::NPAIR };
+    enum { K4 = W::K4, STEPS = V::STEPS, NP = V::NPAIR, FILL = HALF ? 15 : 31 };
     GOTOH_DYN_SMEM(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, plane = threadIdx.x & 31;
+    const int lane = HALF ? (plane & 15) : plane;       // lane within its wavefront
+    const int sub = HALF ? (plane >> 4) : 0;
     unsigned char* my_smem = smem_raw + (size_t)warp * FwdSmem<V, K>::per_warp(p.ncls);
     uint4* prof = reinterpret_cast<uint4*>(my_smem);
 
@@ -497,8 +521,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
     w.four = p.four;
     w.one = p.four >> 2;
     w.z4 = (NP == 2) ? p.zshift : 0;
-    w.prof_lane = prof + lane;
-    w.ring = reinterpret_cast<int2*>(my_smem + (size_t)p.ncls * K4 * 32 * 16);  // [2][32]
+    w.prof_lane = W::USE2 ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(prof) + plane) : prof + plane;
+    w.ring = reinterpret_cast<int2*>(my_smem + FwdSmem<V, K>::prof_bytes(p.ncls));  // [2][32]
     const int u4 = -4 * p.gip;
     w.c_up = V::both(u4 + 1);          // P^ = max(S^up + 4u+1, P^up)
     w.c_sl0 = V::both(u4 + w.z4);          // column 0 seen by the Q recurrence: s~ = u   (gotoh.cpp:291)
@@ -513,10 +537,10 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
         // ---- dynamic task fetch (one atomic per warp) ---------------------------------------
         if (p.task_limit > 0 && done >= p.task_limit) break;
         unsigned tsk = 0;
-        if (lane == 0) tsk = atomicAdd(p.work_counter, 1u);
+        if (plane == 0) tsk = atomicAdd(p.work_counter, 1u);
         tsk = __shfl_sync(0xffffffffu, tsk, 0);
         if (tsk >= (unsigned)p.task_count) break;
-        const Task task = p.tasks[p.task_first + tsk];
+        const Task task = p.tasks[p.task_first + (HALF ? 2 * tsk + sub : tsk)];
         const PairInfo pa = p.pairs[task.pair_a];
         const PairInfo pb = p.pairs[task.pair_b >= 0 ? task.pair_b : task.pair_a];
         const int M = pa.M;                       // both halves share the reference
@@ -533,7 +557,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
         w.lr_j_a = w.lr_j_b = 0;
 
         for (int strip = 0; strip < nstrips; ++strip) {
-            const int j0 = (strip * 32 + lane) * K;           // this lane owns columns j0+1 .. j0+K
+            const int j0 = (strip * 32 + lane) * K;           // this lane owns columns j0+1 .. j0+K (HALF: strip = 0)
             w.strip = strip;
             w.j0 = j0;
             w.last_strip = (strip == nstrips - 1);
@@ -561,25 +585,35 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
                     if (NP == 2) cm_b[k] = stop_mask(qb, Nb, j0 + k + 1);
                 }
             }
+            // the query bytes of this lane's columns, read once (-1: padding column)
+            int qca[K], qcb[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int ja = j0 + k;
+                qca[k] = ja < Na ? (int)qa[ja] : -1;
+                qcb[k] = (NP == 2 && ja < Nb) ? (int)qb[ja] : -1;
+            }
             for (int c = 0; c < p.ncls; ++c) {
                 const int32_t* trow = p.table4 + c * 128;
                 const int32_t* brow = p.bonus4 + c * 8;
+                unsigned e[K4 * 4];
 #pragma unroll
-                for (int kq = 0; kq < K4; ++kq) {
-                    unsigned e[4];
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int k = kq * 4 + kk;
-                        const int ja = j0 + k;
-                        // padding columns (beyond N) use E = 4u so that they clone column N
-                        int ea = u4, eb = u4;
-                        if (k < K) {
-                            if (ja < Na) ea = trow[qa[ja]] + (p.has_dollar ? brow[cm_a[k]] : 0);
-                            if (NP == 2 && ja < Nb) eb = trow[qb[ja]] + (p.has_dollar ? brow[cm_b[k]] : 0);
-                        }
-                        e[kk] = V::lin(ea, NP == 2 ? eb : 0);
+                for (int k = 0; k < K4 * 4; ++k) {
+                    // padding columns (beyond N) use E = 4u so that they clone column N
+                    int ea = u4, eb = u4;
+                    if (k < K) {
+                        if (qca[k] >= 0) ea = trow[qca[k]] + (p.has_dollar ? brow[cm_a[k]] : 0);
+                        if (NP == 2 && qcb[k] >= 0) eb = trow[qcb[k]] + (p.has_dollar ? brow[cm_b[k]] : 0);
                     }
-                    prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
+                    e[k] = V::lin(ea, NP == 2 ? eb : 0);
+                }
+                if (W::USE2) {
+                    uint2* prof2 = reinterpret_cast<uint2*>(prof);
+#pragma unroll
+                    for (int kp = 0; kp < W::E2; ++kp) prof2[(c * W::E2 + kp) * 32 + plane] = make_uint2(e[2 * kp], e[2 * kp + 1]);
+                } else {
+#pragma unroll
+                    for (int kq = 0; kq < K4; ++kq) prof[(c * K4 + kq) * 32 + plane] = make_uint4(e[4 * kq], e[4 * kq + 1], e[4 * kq + 2], e[4 * kq + 3]);
                 }
             }
             __syncwarp();
@@ -590,14 +624,14 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
             w.row0_init();                              // lane 0 starts at row 1 in the very first step
             w.next_cls = w.cls[-lane];                  // class of row i = 1 - lane (padding when i < 1)
 
-            uint4* dst = p.dir + pa.dir_off + (int64_t)strip * nblk * 32 + lane;
+            uint4* dst = p.dir + pa.dir_off + (int64_t)strip * nblk * 32 + plane;
             for (int tb = 0; tb < nblk; ++tb, dst += 32) {
                 // Which per-lane events can occur in steps t0 .. hi of this block (rows t-31 .. t)?
                 const int t0 = tb * STEPS + 1, hi = t0 + STEPS - 1;
-                bool slow = (t0 <= 31) || (hi >= M);                    // row 0 re-init / row M capture, i <= M
+                bool slow = (t0 <= FILL) || (hi >= M);                    // row 0 re-init / row M capture, i <= M
                 if (NP == 2) {
                     const int m = hi & ~p.rebase_mask;                  // largest multiple of R that is <= hi
-                    slow = slow || (m > 0 && m >= t0 - 31);             // some lane crosses a rebase row
+                    slow = slow || (m > 0 && m >= t0 - FILL);             // some lane crosses a rebase row
                 }
                 if (slow) w.template block<true>(tb, dst);
                 else w.template block<false>(tb, dst);
@@ -608,7 +642,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
         // last row: reduce (score, j) with larger j winning ties
         int lr_best_a = w.lr_best_a, lr_j_a = w.lr_j_a, lr_best_b = w.lr_best_b, lr_j_b = w.lr_j_b;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
+        for (int off = HALF ? 8 : 16; off > 0; off >>= 1) {
             const int os = __shfl_xor_sync(0xffffffffu, lr_best_a, off);
             const int oj = __shfl_xor_sync(0xffffffffu, lr_j_a, off);
             if (os > lr_best_a || (os == lr_best_a && oj > lr_j_a)) { lr_best_a = os; lr_j_a = oj; }
@@ -622,8 +656,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
         {
             const int i_fin = nblk * STEPS - lane;          // > 0: nblk*STEPS >= M + 31
             const int roff = (NP == 2) ? (i_fin & p.rebase_mask) : i_fin;   // i_fin - base(i_fin)
-            const int la = (Na - 1) / K - (nstrips - 1) * 32;   // owner lane within the last strip
-            const int lb = (Nb - 1) / K;
+            const int la = (Na - 1) / K - (nstrips - 1) * 32 + 16 * sub;   // owner lane within the last strip
+            const int lb = (Nb - 1) / K + 16 * sub;
             int best_a = ((V::lo(w.best) - w.z4) >> 2) - (roff + Na) * p.gep;
             int best_b = ((V::hi(w.best) - w.z4) >> 2) - (roff + Nb) * p.gep;
             best_a = __shfl_sync(0xffffffffu, best_a, la);

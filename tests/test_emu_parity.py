@@ -10,13 +10,16 @@ import pytest
 from conftest import load_golden, run_cases
 
 
-@pytest.fixture(params=["auto", "32"])
+@pytest.fixture(params=["auto", "32", "full"])
 def forced_path(request, monkeypatch):
-    """auto: int16x2 path wherever the range proof allows; 32: everything on the int32 path."""
+    """auto: int16x2 path wherever the range proof allows (two 16-lane wavefronts per warp for queries <= 128 wide);
+    32: everything on the int32 path; full: int16x2 on 32-lane wavefronts only (GOTOH_B200_HALF=0)."""
+    monkeypatch.delenv("GOTOH_B200_FORCE_PATH", raising=False)
+    monkeypatch.delenv("GOTOH_B200_HALF", raising=False)
     if request.param == "32":
         monkeypatch.setenv("GOTOH_B200_FORCE_PATH", "32")
-    else:
-        monkeypatch.delenv("GOTOH_B200_FORCE_PATH", raising=False)
+    elif request.param == "full":
+        monkeypatch.setenv("GOTOH_B200_HALF", "0")
     return request.param
 
 
@@ -105,6 +108,39 @@ def test_emu_mixed_int16x2_and_int32_launches_share_a_plan(emu_aligner, oracle_p
     plan = emu_aligner.plan(rb, ro, None, qb, qo, 40, 10, 1, 0)
     assert plan.stat(5) > 0 and plan.stat(6) > 0, (plan.stat(5), plan.stat(6))
     plan.close()
+
+
+def _half_warp_batch(n, seed):
+    """aa windows of ragged width (1..128: every K of the half-warp kernels) against PR/RT/INT in uneven proportions, so
+    that warps get two couples, one couple + filler, and single pairs; plus nt reads cut to <= 128 columns."""
+    from gotoh_b200 import workloads
+    rng = random.Random(seed)
+    refs, qs = workloads.c3_queries(n, seed=seed)
+    pairs = []
+    for k, q in enumerate(qs):
+        r = refs[0] if k % 7 == 0 else refs[1] if k % 3 else refs[2]
+        w = rng.choice([1, 2, 16, 17, 31, 32, 33, 47, 48, 49, 64, 65, 84, 95, 96, 97, 120, 128])
+        pairs.append((r, (q * 2)[:w]))
+    return pairs
+
+
+def test_emu_half_warp_wavefronts(emu_aligner, oracle_port, monkeypatch):
+    pairs = _half_warp_batch(151, 31)
+    for arena_mb in (None, "1"):                      # "1": the arena is cut into many chunks between the warps' slabs
+        if arena_mb:
+            monkeypatch.setenv("GOTOH_B200_ARENA_MB", arena_mb)
+        for gip, gep, term in [(40, 10, 1), (40, 10, 0), (3, 1, 1)]:
+            got = emu_aligner.align_batch([a for a, _ in pairs], [b for _, b in pairs], gip, gep, term, 1)
+            for (a, b), g in zip(pairs, got):
+                assert g == oracle_port.align_it_aa(a, b, gip, gep, term), (a, b, gip, gep, term)
+    monkeypatch.delenv("GOTOH_B200_ARENA_MB", raising=False)
+    from gotoh_b200 import workloads
+    ref, reads = workloads.c2_reads(40, seed=5)
+    rng = random.Random(2)
+    qs = [r[:rng.randint(1, 128)] for r in reads]
+    got = emu_aligner.align_batch(ref[200:900], qs, 10, 3, 1, 0)
+    for q, g in zip(qs, got):
+        assert g == oracle_port.align_it(ref[200:900], q, 10, 3, 1)
 
 
 def test_emu_many_reference_byte_classes(emu_aligner, oracle_port):

@@ -11,12 +11,16 @@ from conftest import load_golden, run_cases
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["auto", "32"])
+@pytest.fixture(params=["auto", "32", "full"])
 def forced_path(request, monkeypatch):
+    """auto: int16x2 path wherever the range proof allows (two 16-lane wavefronts per warp for queries <= 128 wide);
+    32: everything on the int32 path; full: int16x2 on 32-lane wavefronts only (GOTOH_B200_HALF=0)."""
+    monkeypatch.delenv("GOTOH_B200_FORCE_PATH", raising=False)
+    monkeypatch.delenv("GOTOH_B200_HALF", raising=False)
     if request.param == "32":
         monkeypatch.setenv("GOTOH_B200_FORCE_PATH", "32")
-    else:
-        monkeypatch.delenv("GOTOH_B200_FORCE_PATH", raising=False)
+    elif request.param == "full":
+        monkeypatch.setenv("GOTOH_B200_HALF", "0")
     return request.param
 
 
@@ -115,6 +119,29 @@ def test_gpu_random_fuzz_batch(gpu_aligner, oracle_port, forced_path):
         rb, ro = packing.pack(refs)
         qb, qo = packing.pack(qs)
         _check_packed(gpu_aligner, oracle_port, 0, rb, ro, None, qb, qo, gip, gep, term)
+
+
+def test_gpu_half_warp_wavefronts(gpu_aligner, oracle_port, monkeypatch):
+    """Queries <= 128 wide run as two 16-lane wavefronts per warp (four alignments): ragged widths, uneven reference
+    shares (couple + filler warps), chunked arenas; checked against the oracle, and 200k C3 windows against the
+    32-lane kernels (GOTOH_B200_HALF=0), an independent implementation of the same cells."""
+    from test_emu_parity import _half_warp_batch
+    from gotoh_b200 import packing, workloads
+    pairs = _half_warp_batch(4001, 33)
+    for arena_mb in (None, "2"):
+        if arena_mb:
+            monkeypatch.setenv("GOTOH_B200_ARENA_MB", arena_mb)
+        for gip, gep, term in [(40, 10, 1), (3, 1, 0)]:
+            got = gpu_aligner.align_batch([a for a, _ in pairs], [b for _, b in pairs], gip, gep, term, 1)
+            for (a, b), g in zip(pairs, got):
+                assert g == oracle_port.align_it_aa(a, b, gip, gep, term), (a, b, gip, gep, term)
+    monkeypatch.delenv("GOTOH_B200_ARENA_MB", raising=False)
+    refs, ridx, qb, qo = workloads.c3_queries_packed(200000, seed=9)
+    rb, ro = packing.pack(refs)
+    a = gpu_aligner.align_packed(rb, ro, ridx, qb, qo, 40, 10, 1, 1)
+    monkeypatch.setenv("GOTOH_B200_HALF", "0")
+    b = gpu_aligner.align_packed(rb, ro, ridx, qb, qo, 40, 10, 1, 1)
+    assert (a[3] == b[3]).all() and (a[4] == b[4]).all() and (a[0] == b[0]).all() and (a[1] == b[1]).all()
 
 
 def test_gpu_paths_agree_and_order_invariance_at_scale(gpu_aligner, monkeypatch):

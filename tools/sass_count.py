@@ -103,12 +103,17 @@ def count(kernel_pat, steps, k, npair, shfl="SHFL.UP", per_step=2):
 
 
 def main():
-    x2 = count("k_forwardINS_5Vec16ELi8ELb0", 4, 8, 2)
-    x1 = count("k_forwardINS_5Vec32ELi8ELb0", 8, 8, 1)
+    x2 = count("k_forwardINS_5Vec16ELi8ELb0ELb0E", 4, 8, 2)
+    x1 = count("k_forwardINS_5Vec32ELi8ELb0ELb0E", 8, 8, 1)
     doc = {"_how": "tools/sass_count.py over cuobjdump -sass of micall-lite_b200/lib/libgotoh_b200.so (steady-state block)",
            "x2": x2, "x1": x1,
            "instr_per_cell_x2": x2["instr_per_cell"], "alu_per_cell_x2": x2["alu_per_cell"], "fma_per_cell_x2": x2["fma_per_cell"],
            "instr_per_cell_x1": x1["instr_per_cell"], "alu_per_cell_x1": x1["alu_per_cell"], "fma_per_cell_x1": x1["fma_per_cell"]}
+    # half-warp wavefronts (queries <= 128 wide; C3 runs K = 6)
+    try:
+        doc["x2_half_k6"] = count("k_forwardINS_5Vec16ELi6ELb0ELb1E", 4, 6, 2)
+    except Exception as e:
+        doc["x2_half_k6"] = {"error": str(e)}
     # gotoh2 (live aligner) kernels: forward with tie bits, score-only forward, reverse sweep (4 lane-steps x 8 columns)
     for tag, pat, sh, per, npair in (("g2_forward", "k2fILi8ELb0ELb1", "SHFL.UP", 2, 1), ("g2_forward_score_only", "k2fILi8ELb0ELb0", "SHFL.UP", 2, 1),
                                      ("g2_forward_x2", "k2f_x2ILi8E", "SHFL.UP", 2, 2), ("g2_reverse", "k2rILi8ELb0", "SHFL.DOWN", 1, 1)):
@@ -127,7 +132,7 @@ def main():
             pass
     os.makedirs(os.path.dirname(prev), exist_ok=True)
     json.dump(doc, open(prev, "w"), indent=1)
-    for tag in ("x2", "x1", "g2_forward", "g2_forward_score_only", "g2_forward_x2", "g2_reverse"):
+    for tag in ("x2", "x1", "x2_half_k6", "g2_forward", "g2_forward_score_only", "g2_forward_x2", "g2_reverse"):
         d = doc[tag]
         if "error" in d:
             print(tag, d["error"])
