@@ -281,6 +281,29 @@ struct KeyIdx {
     bool operator<(const KeyIdx& o) const { return key != o.key ? key < o.key : idx < o.idx; }
 };
 
+// Stable LSD radix sort of (key, idx) records by key, 16 bits per pass, skipping passes whose digit is constant
+// (std::sort was the largest single item of plan_build on batches of short pairs).  Records enter in idx order, so
+// equal keys stay in idx order - the same total order as KeyIdx::operator<.
+void radix_sort(std::vector<KeyIdx>& v) {
+    const size_t n = v.size();
+    if (n < 2048) { std::sort(v.begin(), v.end()); return; }
+    std::vector<KeyIdx> tmp(n);
+    std::vector<uint32_t> cnt(65536);
+    KeyIdx* src = v.data();
+    KeyIdx* dst = tmp.data();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int sh = 16 * pass;
+        std::fill(cnt.begin(), cnt.end(), 0u);
+        for (size_t i = 0; i < n; ++i) ++cnt[(src[i].key >> sh) & 0xffff];
+        if (cnt[(src[0].key >> sh) & 0xffff] == n) continue;        // every record has the same digit
+        uint32_t sum = 0;
+        for (size_t d = 0; d < 65536; ++d) { const uint32_t c = cnt[d]; cnt[d] = sum; sum += c; }
+        for (size_t i = 0; i < n; ++i) dst[cnt[(src[i].key >> sh) & 0xffff]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != v.data()) memcpy(v.data(), src, n * sizeof(KeyIdx));
+}
+
 // Run fn(lo, hi, tid) over [0, n) on up to `threads` host threads.
 template <class F>
 void parallel_for(int64_t n, int threads, F fn) {
@@ -459,10 +482,12 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     std::vector<HostPair> hp((size_t)n);
     const int64_t qbytes_in = qry_off[pair_end] - qry_off[pair_begin];
     const int nthreads = host_threads(qbytes_in);
-    struct ThreadErr { int code = 0; int64_t pair = -1; int byte = 0; bool present[128] = {false}; int64_t cells = 0; };
+    struct ThreadErr { int code = 0; int64_t pair = -1; int byte = 0; uint64_t mask[2] = {0, 0}; int64_t cells = 0; char pad[64]; };   // mask: bytes 0-63, 64-127 seen
     std::vector<ThreadErr> terr((size_t)nthreads);
     parallel_for(n, nthreads, [&](int64_t lo_k, int64_t hi_k, int tid) {
         ThreadErr& te = terr[(size_t)tid];
+        uint8_t unk[256];
+        memset(unk, 1, sizeof(unk));
         for (int64_t kk = lo_k; kk < hi_k; ++kk) {
             const int64_t k = pair_begin + kk;
             HostPair& h = hp[(size_t)kk];
@@ -471,14 +496,33 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
             int64_t lo, hi;
             trim_span(s, qry_off[k + 1] - qry_off[k], &lo, &hi);
             if (hi - lo >= (1 << 24)) { if (!te.code) { te.code = GOTOH_B200_ERANGE; te.pair = k; } return; }
-            int nn = 0;
-            unsigned bad = 0;
-            for (int64_t x = lo; x < hi; ++x) {
-                const uint8_t c = s[x];
-                bad |= (unsigned)((uint8_t)(c - 1) > 125);
-                te.present[c & 127] = true;
-                nn += !(degap && c == '-');
+            // Which bytes occur (the score range of the int16 proof depends on it) and are they all in 1..126?  Each
+            // thread keeps the set it has already seen as a 256-entry table `unk` (1 = not seen yet / invalid): a query
+            // made of known bytes costs one table load and one OR per byte; only a query that brings a new byte (the
+            // first few of a batch) or an invalid one takes the exact loop below.
+            unsigned fresh = 0;
+            {
+                unsigned f0 = 0, f1 = 0, f2 = 0, f3 = 0;          // independent chains: the loop is load-bound, not OR-bound
+                int64_t x = lo;
+                for (; x + 8 <= hi; x += 8) {
+                    f0 |= unk[s[x]] | unk[s[x + 4]]; f1 |= unk[s[x + 1]] | unk[s[x + 5]];
+                    f2 |= unk[s[x + 2]] | unk[s[x + 6]]; f3 |= unk[s[x + 3]] | unk[s[x + 7]];
+                }
+                for (; x < hi; ++x) f0 |= unk[s[x]];
+                fresh = f0 | f1 | f2 | f3;
             }
+            unsigned bad = 0;
+            if (fresh) {
+                for (int64_t x = lo; x < hi; ++x) {
+                    const unsigned c = s[x];
+                    if ((uint8_t)(c - 1) > 125) { bad = 1; continue; }
+                    unk[c] = 0;
+                    te.mask[c >> 6] |= 1ull << (c & 63);
+                }
+            }
+            int dashes = 0;
+            if (degap) for (int64_t x = lo; x < hi; ++x) dashes += (s[x] == '-');
+            const int nn = (int)(hi - lo) - (degap ? dashes : 0);
             if (bad) {
                 if (!te.code) {
                     te.code = GOTOH_B200_EDOMAIN; te.pair = k;
@@ -510,7 +554,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         if (te.code == GOTOH_B200_ESENTINEL) return fail(te.code, "pair %lld: 2*gip+(max(M,N)+1)*gep >= 100000 (sentinel domain, gotoh.cpp:284)", (long long)te.pair);
         if (te.code == GOTOH_B200_ERANGE) return fail(te.code, te.byte == -1 ? "pair %lld: output stride smaller than M+N (or >= 2^31)" : "query %lld too long", (long long)te.pair);
         if (te.code) return fail(te.code, "qry_off not monotone at %lld", (long long)te.pair);
-        for (int c = 0; c < 128; ++c) qry_present[c] |= te.present[c];
+        for (int c = 0; c < 128; ++c) qry_present[c] |= (bool)((te.mask[c >> 6] >> (c & 63)) & 1);
         pl->cells += te.cells;
     }
     phase(1);
@@ -625,17 +669,24 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     }
     int R = 32;
     if (!elig.empty()) {
+        // fits_int16 depends on the pair through min(M,N) and K only and is monotone in min(M,N): test, per K, the
+        // eligible pair with the largest min(M,N) instead of every pair for every candidate
+        int worst_mn[kMaxK + 1];
+        for (int k = 0; k <= kMaxK; ++k) worst_mn[k] = -1;
+        for (const KeyIdx& ki : elig) {
+            const HostPair& h = hp[ki.idx];
+            const int K = pick_K(h.N);
+            worst_mn[K] = std::max(worst_mn[K], std::min(h.M, h.N));
+        }
         for (int cand = 4096; cand >= 32; cand >>= 1) {
             bool all = true;
-            for (const KeyIdx& ki : elig) {
-                const HostPair& h = hp[ki.idx];
-                if (!fits_int16(h.M, h.N, pick_K(h.N), cand, pl->gip, pl->gep, minT, maxT, z4)) { all = false; break; }
-            }
+            for (int k = 0; k <= kMaxK && all; ++k)
+                if (worst_mn[k] >= 0 && !fits_int16(worst_mn[k], worst_mn[k], k, cand, pl->gip, pl->gep, minT, maxT, z4)) all = false;
             if (all) { R = cand; break; }
         }
     }
     phase(4);
-    std::sort(elig.begin(), elig.end());
+    radix_sort(elig);
     std::sort(wide.begin(), wide.end());
     phase(5);
 
@@ -858,6 +909,11 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     CU(h2d(ws->d_tasks.p, tasks, n_tasks * sizeof(Task)));
     if (pl->n_stasks) CU(h2d(ws->d_stasks.p, ws->h_stasks.p, (size_t)pl->n_stasks * sizeof(Task)));
     phase(7);
+    if (trace_on() && !pl->owns_ws)
+        ;   // the one-shot call prints the phases per slab
+    else if (trace_on())
+        fprintf(stderr, "[gotoh_b200] plan_build %lld pairs: refs %.2f pass1 %.2f pass2 %.2f cls %.2f path %.2f sort %.2f tasks %.2f alloc+h2d %.2f ms\n",
+                (long long)n, g_trace_phase[0], g_trace_phase[1], g_trace_phase[2], g_trace_phase[3], g_trace_phase[4], g_trace_phase[5], g_trace_phase[6], g_trace_phase[7]);
     return GOTOH_B200_OK;
 }
 
@@ -1136,6 +1192,7 @@ extern "C" int32_t gotoh_b200_plan_create(int32_t device, const uint8_t* ref_byt
     pl->owns_ws = true;
     pl->gip = gip; pl->gep = gep; pl->term = use_terminal ? 1 : 0; pl->matrix = matrix_id;
     rc = ws->init(device);
+    for (double& x : g_trace_phase) x = 0;
     if (!rc) {
         try {
             rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, 0, n_pairs, out_off);
