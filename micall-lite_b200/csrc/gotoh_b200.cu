@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -125,6 +126,7 @@ struct Workspace {
     bool ready = false;
     cudaStream_t stream = 0;
     cudaEvent_t ev[4] = {0, 0, 0, 0};
+    cudaEvent_t ev_fwd = 0;    // one-shot pipeline: recorded after the forward launches of the slab this workspace holds
     int trace_slab = -1;       // GOTOH_B200_TRACE: slab whose events ev[0..2] are pending
     int sm_count = 1;
     // device
@@ -153,6 +155,7 @@ struct Workspace {
         sm_count = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&ev[i]));
+        CU(cudaEventCreateWithFlags(&ev_fwd, cudaEventDisableTiming));
         ready = true;
         return GOTOH_B200_OK;
     }
@@ -167,6 +170,7 @@ struct Workspace {
         d_counter.release();
         h_ref_raw.release(); h_ref_cls.release(); h_qry.release(); h_pairs.release(); h_tasks.release(); h_table4.release();
         for (int i = 0; i < 4; ++i) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = 0; }
+        if (ev_fwd) { cudaEventDestroy(ev_fwd); ev_fwd = 0; }
         if (stream) { cudaStreamDestroy(stream); stream = 0; }
         ready = false;
     }
@@ -199,6 +203,7 @@ struct gotoh_b200_plan {
     int has_dollar = 0;
     int smin_m1 = 0;
     int zshift = 0;        // Vec16 frame shift (fits_int16)
+    bool mark_forward_done = false;   // one-shot pipeline: record ws->ev_fwd after the last forward launch
     std::vector<Chunk> chunks;
     int n_launches = 0;
     int64_t out_base = 0, out_bytes = 0;   // caller's out_off range covered by this plan
@@ -978,6 +983,7 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
             if (rc) return rc;
         }
         if (timed && forward_ms) CU(cudaEventRecord(ws->ev[3], ws->stream));
+        if (pl->mark_forward_done && ci + 1 == pl->chunks.size()) CU(cudaEventRecord(ws->ev_fwd, ws->stream));
         WalkParams wp;
         memset(&wp, 0, sizeof(wp));
         wp.pairs = ws->d_pairs.p; wp.pair_first = c.pair_first; wp.pair_count = c.pair_count;
@@ -1064,6 +1070,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
                      const int32_t* ref_idx, const uint8_t* qry_bytes, const int64_t* qry_off,
                      int64_t lo, int64_t hi, int32_t gip, int32_t gep, int32_t term, int32_t matrix_id,
                      uint8_t* out_ref, uint8_t* out_qry, const int64_t* out_off, int32_t* out_len, int32_t* out_score) {
+    const double t_entry = now_ms();
     DeviceCtx* ctx = ctx_for(dev);
     if (!ctx) return fail(GOTOH_B200_ENOMEM, "out of host memory");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1107,6 +1114,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
         k = e;
     }
     const int nslabs = (int)cuts.size() - 1;
+    const double t_cuts = now_ms();
     if (trace_on()) { cudaEventRecord(ctx->ws[0].ev[3], ctx->ws[0].stream); cudaEventSynchronize(ctx->ws[0].ev[3]); for (int w = 0; w < NWS; ++w) ctx->ws[w].trace_slab = -1; }
     // Two builder threads pack alternate slabs (each owns half of the workspaces), so the host's packing rate is
     // not the pipeline's bottleneck: per slab the host needs about as long as the kernels (measured on B200).
@@ -1115,8 +1123,18 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     std::vector<int> rcs((size_t)builders, 0);
     std::vector<std::string> msgs((size_t)builders);
     std::atomic<int> failed(0);
+    // Kernels are ENQUEUED in slab order (the builders pack in parallel, then take turns), and the forward kernel of slab
+    // s waits for the forward kernel of slab s - depth: without this all slabs in flight time-slice the SMs, finish
+    // together and then queue up on the copy engine while the builders - waiting for a drained workspace - leave the
+    // GPU idle (B200 trace: 30 ms of a 173 ms call).  depth = 2 keeps one more forward kernel resident to fill the tail
+    // of the one ahead; walk/emit/D2H of a slab overlap the forward kernels of the next ones.
+    int depth = getenv("GOTOH_B200_FWD_DEPTH") ? atoi(getenv("GOTOH_B200_FWD_DEPTH")) : 2;
+    std::mutex order_mu;
+    std::condition_variable order_cv;
+    int next_enqueue = 0;
+    std::vector<int> slab_ws((size_t)nslabs, -1);
     auto builder = [&](int b) {
-        if (cudaSetDevice(dev) != cudaSuccess) { rcs[(size_t)b] = GOTOH_B200_ECUDA; msgs[(size_t)b] = "cudaSetDevice failed"; failed = 1; return; }
+        if (cudaSetDevice(dev) != cudaSuccess) { rcs[(size_t)b] = GOTOH_B200_ECUDA; msgs[(size_t)b] = "cudaSetDevice failed"; failed = 1; order_cv.notify_all(); return; }
         int mine = 0;
         for (int slab = b; slab < nslabs && !failed.load(); slab += builders, ++mine) {
             // builder b owns workspaces b, b+builders, ...; its previous slab on that workspace must have drained
@@ -1143,8 +1161,22 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
                 }
             }
             const double t_c = now_ms();
-            if (trace_on() && !rc) cudaEventRecord(pl->ws->ev[0], pl->ws->stream);
-            if (!rc) rc = plan_run(pl, false, nullptr, nullptr);
+            {
+                std::unique_lock<std::mutex> lk(order_mu);
+                order_cv.wait(lk, [&] { return next_enqueue == slab || failed.load(); });
+                if (!rc && !failed.load()) {
+                    slab_ws[(size_t)slab] = (int)(pl->ws - &ctx->ws[0]);
+                    if (depth > 0 && slab - depth >= 0 && slab_ws[(size_t)(slab - depth)] >= 0 &&
+                        cudaStreamWaitEvent(pl->ws->stream, ctx->ws[slab_ws[(size_t)(slab - depth)]].ev_fwd, 0) != cudaSuccess)
+                        rc = fail(GOTOH_B200_ECUDA, "cudaStreamWaitEvent failed");
+                    pl->mark_forward_done = true;
+                    if (trace_on() && !rc) cudaEventRecord(pl->ws->ev[0], pl->ws->stream);
+                    if (!rc) rc = plan_run(pl, false, nullptr, nullptr);
+                }
+                next_enqueue = slab + 1;
+                if (rc) failed = 1;
+                order_cv.notify_all();
+            }
             if (trace_on() && !rc) cudaEventRecord(pl->ws->ev[1], pl->ws->stream);
             if (!rc) rc = plan_fetch(pl, out_ref, out_qry, out_len, out_score);
             if (trace_on() && !rc) { cudaEventRecord(pl->ws->ev[2], pl->ws->stream); pl->ws->trace_slab = slab; }
@@ -1162,12 +1194,16 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
         for (auto& t : th) t.join();
     }
     int rc = GOTOH_B200_OK;
+    const double t_built = now_ms();
     for (int b = 0; b < builders; ++b)
         if (rcs[(size_t)b] && !rc) rc = fail(rcs[(size_t)b], "%s", msgs[(size_t)b].c_str());
     for (int w = 0; w < nws; ++w) {
         const cudaError_t e = cudaStreamSynchronize(ctx->ws[w].stream);
         if (e != cudaSuccess && !rc) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
     }
+    if (trace_on())
+        fprintf(stderr, "[gotoh_b200] dev %d call: setup+cuts %.2f ms (%d slabs), builders %.2f ms, drain %.2f ms\n", dev, t_cuts - t_entry, nslabs,
+                t_built - t_cuts, now_ms() - t_built);
     return rc;
 }
 
