@@ -362,24 +362,21 @@ struct Wave {
         Sd_in = Sl;
 
         // ---- K cells of row i ------------------------------------------------------------------
-        unsigned evs[K4 * 4];
-        if (USE2) {
-            const uint2* prow = reinterpret_cast<const uint2*>(prof_lane) + my_cls * (E2 * 32);
-#pragma unroll
-            for (int kp = 0; kp < E2; ++kp) { const uint2 e2 = prow[kp * 32]; evs[2 * kp] = e2.x; evs[2 * kp + 1] = e2.y; }
-        } else {
-            const uint4* prow = prof_lane + my_cls * (K4 * 32);
-#pragma unroll
-            for (int kq = 0; kq < K4; ++kq) {
-                const uint4 e4 = prow[kq * 32];
-                evs[4 * kq] = e4.x; evs[4 * kq + 1] = e4.y; evs[4 * kq + 2] = e4.z; evs[4 * kq + 3] = e4.w;
-            }
-        }
+        const uint4* prow = prof_lane + my_cls * (K4 * 32);
+        const uint2* prow2 = reinterpret_cast<const uint2*>(prof_lane) + my_cls * (E2 * 32);   // K = 2, 6: rows of uint2
         T sleft = Sl, q = Ql;
         unsigned accC = 0, accS = 0;
 #pragma unroll
         for (int kq = 0; kq < K4; ++kq) {
-            const unsigned* ev = evs + 4 * kq;
+            unsigned ev[4] = {0u, 0u, 0u, 0u};
+            if (USE2) {
+                const uint2 a2 = prow2[(2 * kq) * 32];
+                ev[0] = a2.x; ev[1] = a2.y;
+                if (2 * kq + 1 < E2) { const uint2 b2 = prow2[(2 * kq + 1) * 32]; ev[2] = b2.x; ev[3] = b2.y; }
+            } else {
+                const uint4 e4 = prow[kq * 32];
+                ev[0] = e4.x; ev[1] = e4.y; ev[2] = e4.z; ev[3] = e4.w;
+            }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const int k = kq * 4 + kk;
@@ -602,8 +599,14 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
                     // padding columns (beyond N) use E = 4u so that they clone column N
                     int ea = u4, eb = u4;
                     if (k < K) {
-                        if (qca[k] >= 0) ea = trow[qca[k]] + (p.has_dollar ? brow[cm_a[k]] : 0);
-                        if (NP == 2 && qcb[k] >= 0) eb = trow[qcb[k]] + (p.has_dollar ? brow[cm_b[k]] : 0);
+                        const int ja = j0 + k;
+                        if (HALF) {
+                            if (qca[k] >= 0) ea = trow[qca[k]] + (p.has_dollar ? brow[cm_a[k]] : 0);
+                            if (NP == 2 && qcb[k] >= 0) eb = trow[qcb[k]] + (p.has_dollar ? brow[cm_b[k]] : 0);
+                        } else {
+                            if (ja < Na) ea = trow[qa[ja]] + (p.has_dollar ? brow[cm_a[k]] : 0);
+                            if (NP == 2 && ja < Nb) eb = trow[qb[ja]] + (p.has_dollar ? brow[cm_b[k]] : 0);
+                        }
                     }
                     e[k] = V::lin(ea, NP == 2 ? eb : 0);
                 }
