@@ -766,6 +766,127 @@ __global__ void __launch_bounds__(128, 8) k2r(const Params p) {
 }
 
 // -------------------------------------------------------------------------------------------------------
+// reverse sweep, two pairs per warp (K <= 3, single strip, pairs that share seq1)
+// -------------------------------------------------------------------------------------------------------
+// The reverse sweep costs ~66 instructions per lane-step whatever K is - it is bit-parallel over a lane's columns - so at
+// K = 3 (84-column amino-acid windows) a cell costs 22 instructions.  Every plane of a lane then uses 3 bits of a byte:
+// a second pair fits the other nibble (column k of pair B at bit 4 + K-1-k), every operation of Rev::step is bitwise except
+// the carry-chain addition, and two K-bit operands plus a carry-in sum to at most 15, so nothing crosses from one nibble
+// into the next.  The couples are the ones the int16x2 forward kernel formed (same seq1, same K, hence the same rows and
+// blocks); a single pair rides along with a copy of itself.
+template <int K>
+struct Rev2 {
+    static_assert(K <= 3, "two K-bit operands + carry must fit a nibble");
+    enum { KMASK = (1 << K) - 1, KM2 = KMASK | (KMASK << 4) };
+    int lane, M;
+    unsigned colmask, sent_last, sent_rows;          // nibble-packed: pair A | pair B << 4
+    unsigned finA_dn, finC_dn, DE_dn;
+    unsigned send;
+
+    template <bool SLOW>
+    __device__ __forceinline__ unsigned step(const int t, const unsigned wlA, const unsigned whA, const unsigned wlB, const unsigned whB) {
+        const int i = t - lane;
+        const bool valid = !SLOW || (i >= 1 && i <= M);
+        const unsigned m8 = valid ? colmask : 0u;
+        const unsigned sent = (SLOW && i == M) ? sent_last : sent_rows;
+        // pair B's 2-bit codes move up by 8 bit positions: compress_even then drops them into the high nibble
+        const unsigned wl = wlA | (wlB << 8);
+        const unsigned even = wl & 0x55555555u, odd = (wl >> 1) & 0x55555555u;
+        const unsigned eg = compress_even(even | odd);            // e | g << 16
+        const unsigned df = compress_even(odd ^ 0x55555555u);     // d | f << 16
+        const unsigned DE = __byte_perm(df, eg, 0x7740) & (m8 * 0x0101u);     // d | e << 8
+        const unsigned FG = __byte_perm(df, eg, 0x7762) & (m8 * 0x0101u);     // f | g << 8
+        const unsigned own = (whA | (whB << 4)) & (m8 * 0x010101u);           // a | b << 8 | c << 16
+        unsigned in = __shfl_down_sync(0xffffffffu, send, 1);
+        if (lane == 31) in = 0;
+        const unsigned FGr = (((FG << 1) & 0xeeeeu) | (in & 0x1111u)) & (KM2 * 0x0101u);
+        const unsigned Fr = FGr & 0xffu, Gr = FGr >> 8;
+        const unsigned cin = (in >> 16) & 0x11u;
+        const unsigned C1 = ((((finC_dn << 1) | ((in >> 24) & 0x11u)) & KM2) | sent) & m8;
+        const unsigned A1 = finA_dn, D_dn = DE_dn & 0xffu, E_dn = DE_dn >> 8;
+        const unsigned ownA = own & 0xffu, ownB = (own >> 8) & 0xffu, ownC = own >> 16;
+        const unsigned K0 = (A1 & E_dn) | C1;
+        const unsigned Gg = ownB & K0, Pp = (ownB & Gr) | Fr;
+        const unsigned x = Gg | Pp;
+        const unsigned cvec = (x + Gg + cin) ^ x ^ Gg;
+        const unsigned finB = (cvec >> 1) & m8;
+        const unsigned keepm = K0 | (cvec & Gr);
+        const unsigned finA = (ownA & keepm) | (A1 & D_dn);
+        const unsigned finC = ownC & keepm;
+        send = ((FG | (finB << 16) | (finC_dn << 24)) >> (K - 1)) & 0x11111111u;
+        finA_dn = finA; finC_dn = finC; DE_dn = DE;
+        return finA | (finB << 8) | (finC << 16);
+    }
+};
+
+// tasks: (pair = first pair, strip = second pair or -1), the list k2f_x2 consumed
+template <int K>
+__global__ void __launch_bounds__(128, 6) k2r_x2(const Params p) {
+    typedef Rev2<K> R;
+    enum { KMASK = R::KMASK };
+    const int lane = threadIdx.x & 31;
+    const unsigned local = p.is_global ? 0u : 1u;
+    R r;
+    r.lane = lane;
+    for (;;) {
+        unsigned tsk = 0;
+        if (lane == 0) tsk = atomicAdd(p.counter_r, 1u);
+        tsk = __shfl_sync(0xffffffffu, tsk, 0);
+        if (tsk >= (unsigned)p.task_count) break;
+        const StripTask task = p.tasks[tsk];
+        const PairInfo pa = p.pairs[task.pair];
+        const PairInfo pb = p.pairs[task.strip >= 0 ? task.strip : task.pair];
+        const int M = pa.M, nblk = pa.nblk;
+        const int j0 = lane * K;
+        unsigned colmask = 0, bitN = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int N = half ? pb.N : pa.N;
+            const int nreal = max(0, min(K, N - j0));
+            const unsigned cm = (unsigned)(KMASK & ~((1 << (K - nreal)) - 1));
+            const unsigned bn = (N > j0 && N <= j0 + K) ? (1u << (K - 1 - (N - j0 - 1))) : 0u;
+            colmask |= cm << (4 * half);
+            bitN |= bn << (4 * half);
+        }
+        r.M = M;
+        r.colmask = colmask;
+        r.sent_last = local ? colmask : bitN;
+        r.sent_rows = local ? bitN : 0u;
+        r.finA_dn = 0; r.finC_dn = 0; r.DE_dn = 0; r.send = 0;
+        const uint4* sloA = p.lo + pa.dir_off + lane;
+        uint4* shiA = p.hi + pa.dir_off + lane;
+        const uint4* sloB = p.lo + pb.dir_off + lane;
+        uint4* shiB = p.hi + pb.dir_off + lane;
+        const unsigned split = KMASK * 0x010101u;
+        uint4 nlA = sloA[(int64_t)(nblk - 1) * 32], nhA = shiA[(int64_t)(nblk - 1) * 32];
+        uint4 nlB = sloB[(int64_t)(nblk - 1) * 32], nhB = shiB[(int64_t)(nblk - 1) * 32];
+        for (int tb = nblk - 1; tb >= 0; --tb) {
+            const int t0 = tb * FSTEPS + 1, thi = t0 + FSTEPS - 1;
+            const uint4 lA = nlA, hA = nhA, lB = nlB, hB = nhB;
+            if (tb > 0) {
+                nlA = sloA[(int64_t)(tb - 1) * 32]; nhA = shiA[(int64_t)(tb - 1) * 32];
+                nlB = sloB[(int64_t)(tb - 1) * 32]; nhB = shiB[(int64_t)(tb - 1) * 32];
+            }
+            uint4 f;
+            if (t0 >= 32 && thi < M) {
+                f.w = r.template step<false>(t0 + 3, lA.w, hA.w, lB.w, hB.w);
+                f.z = r.template step<false>(t0 + 2, lA.z, hA.z, lB.z, hB.z);
+                f.y = r.template step<false>(t0 + 1, lA.y, hA.y, lB.y, hB.y);
+                f.x = r.template step<false>(t0 + 0, lA.x, hA.x, lB.x, hB.x);
+            } else {
+                f.w = r.template step<true>(t0 + 3, lA.w, hA.w, lB.w, hB.w);
+                f.z = r.template step<true>(t0 + 2, lA.z, hA.z, lB.z, hB.z);
+                f.y = r.template step<true>(t0 + 1, lA.y, hA.y, lB.y, hB.y);
+                f.x = r.template step<true>(t0 + 0, lA.x, hA.x, lB.x, hB.x);
+            }
+            shiA[(int64_t)tb * 32] = make_uint4(f.x & split, f.y & split, f.z & split, f.w & split);
+            if (task.strip >= 0)
+                shiB[(int64_t)tb * 32] = make_uint4((f.x >> 4) & split, (f.y >> 4) & split, (f.z >> 4) & split, (f.w >> 4) & split);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
 // traceback
 // -------------------------------------------------------------------------------------------------------
 struct WalkParams {

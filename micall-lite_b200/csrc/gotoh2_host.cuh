@@ -191,6 +191,14 @@ int g2_launch_rev(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
     return 0;
 }
 template <int K>
+int g2_launch_rev_x2(G2Run& run, const gotoh::g2f::Params& p, int ntasks) {
+    using namespace gotoh::g2f;
+    const int grid = std::max(1, std::min((ntasks + 3) / 4, run.sm_count * 6));
+    GOTOH_LAUNCH((k2r_x2<K>), dim3(grid), dim3(128), 0, (cudaStream_t)0, p);
+    CU(cudaGetLastError());
+    return 0;
+}
+template <int K>
 int g2_launch_group(G2Run& run, const gotoh::g2f::Params& p, int ntasks, bool multi, int phase) {
     if (phase == 2) return g2_launch_fwd_x2<K>(run, p, ntasks);
     if (phase == 0) {
@@ -266,7 +274,7 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
     CU(b.part.ensure((size_t)slots_max * 2));
     CU(b.fbnd.ensure((size_t)bnd_max + 1));
     CU(b.rbnd.ensure((size_t)bnd_max + 1));
-    CU(b.counters.ensure(24));
+    CU(b.counters.ensure(40));     // task schedulers: forward [g], reverse [8+g], int16x2 forward [16+g], reverse remainder [24+g]
     CU(cudaMemcpy(b.pairs.p, pairs.data(), n * sizeof(PairInfo), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(b.extra.p, extra.data(), n * sizeof(Extra), cudaMemcpyHostToDevice));
     run.arena_bytes = run.score_only ? 0 : arena_max * 32;
@@ -326,7 +334,7 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
             CU(cudaMemset(b.rbnd.p, 0xff, (size_t)ch.bnd));
         }
         CU(cudaMemset(b.part.p, 0x80, (size_t)ch.slots * sizeof(int32_t)));
-        CU(cudaMemset(b.counters.p, 0, 24 * sizeof(uint32_t)));
+        CU(cudaMemset(b.counters.p, 0, 40 * sizeof(uint32_t)));
         Params p;
         memset(&p, 0, sizeof(p));
         p.pairs = b.pairs.p; p.extra = b.extra.p;
@@ -363,15 +371,29 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
         CU(cudaEventRecord(run.ev.e[1], 0));
         if (!run.score_only) {
             for (size_t g = 0; g < groups.size(); ++g) {
-                p.tasks = b.tasks.p + groups[g].first; p.task_count = groups[g].count;
-                p.counter_r = b.counters.p + 8 + g;
+                // K <= 3: the couples of the int16x2 forward kernel are swept two per warp (k2r_x2), the other pairs of the
+                // group one per warp; GOTOH_B200_GOTOH2=r1 pins the one-pair kernel (tests)
+                const bool r2 = groups[g].x2_count > 0 && groups[g].K <= 3 && !(g2sel && !strcmp(g2sel, "r1"));
+                if (r2) {
+                    p.tasks = b.tasks.p + groups[g].x2_first; p.task_count = groups[g].x2_count;
+                    p.counter_r = b.counters.p + 8 + g;
+                    const int rc = groups[g].K == 2 ? g2_launch_rev_x2<2>(run, p, p.task_count) : g2_launch_rev_x2<3>(run, p, p.task_count);
+                    if (rc) return rc;
+                    ++run.launches;
+                    if (groups[g].f32_count == 0) continue;
+                    p.tasks = b.tasks.p + groups[g].f32_first; p.task_count = groups[g].f32_count;
+                    p.counter_r = b.counters.p + 24 + g;
+                } else {
+                    p.tasks = b.tasks.p + groups[g].first; p.task_count = groups[g].count;
+                    p.counter_r = b.counters.p + 8 + g;
+                }
                 int rc = 0;
                 switch (groups[g].K) {
-                    case 2: rc = g2_launch_group<2>(run, p, groups[g].count, groups[g].multi, 1); break;
-                    case 3: rc = g2_launch_group<3>(run, p, groups[g].count, groups[g].multi, 1); break;
-                    case 4: rc = g2_launch_group<4>(run, p, groups[g].count, groups[g].multi, 1); break;
-                    case 6: rc = g2_launch_group<6>(run, p, groups[g].count, groups[g].multi, 1); break;
-                    default: rc = g2_launch_group<8>(run, p, groups[g].count, groups[g].multi, 1); break;
+                    case 2: rc = g2_launch_group<2>(run, p, p.task_count, groups[g].multi, 1); break;
+                    case 3: rc = g2_launch_group<3>(run, p, p.task_count, groups[g].multi, 1); break;
+                    case 4: rc = g2_launch_group<4>(run, p, p.task_count, groups[g].multi, 1); break;
+                    case 6: rc = g2_launch_group<6>(run, p, p.task_count, groups[g].multi, 1); break;
+                    default: rc = g2_launch_group<8>(run, p, p.task_count, groups[g].multi, 1); break;
                 }
                 if (rc) return rc;
                 ++run.launches;

@@ -146,6 +146,12 @@ def _check_couples(lib, oracle2, monkeypatch, n_reads, n_full):
     assert _x2_tasks(lib) == 0
     for (a, b), o in zip(full, out):
         assert o == oracle2.align(a, b, 10, 10, False, "HYPHY_NUC")
+    # GOTOH_B200_GOTOH2=r1 pins the one-pair-per-warp reverse sweep (K <= 3 couples otherwise share a warp, k2r_x2)
+    monkeypatch.setenv("GOTOH_B200_GOTOH2", "r1")
+    for pairs, gop, gep, glob, model in [(nt, 10, 3, False, "HYPHY_NUC"), (aa, 40, 10, False, "EmpHIV25"), (aa, 40, 10, True, "EmpHIV25")]:
+        al = Aligner(gop, gep, glob, model, library=lib)
+        for (a, b), o in zip(pairs, al.align_batch(pairs)):
+            assert o == oracle2.align(a, b, gop, gep, glob, model), (gop, gep, glob, model, b)
     # GOTOH_B200_GOTOH2=x1 pins the int32 forward kernel: same answers, no couples
     monkeypatch.setenv("GOTOH_B200_GOTOH2", "x1")
     al = Aligner(10, 3, False, "HYPHY_NUC", library=lib)

@@ -116,9 +116,10 @@ def main():
         doc["x2_half_k6"] = {"error": str(e)}
     # gotoh2 (live aligner) kernels: forward with tie bits, score-only forward, reverse sweep (4 lane-steps x 8 columns)
     for tag, pat, sh, per, npair in (("g2_forward", "k2fILi8ELb0ELb1", "SHFL.UP", 2, 1), ("g2_forward_score_only", "k2fILi8ELb0ELb0", "SHFL.UP", 2, 1),
-                                     ("g2_forward_x2", "k2f_x2ILi8E", "SHFL.UP", 2, 2), ("g2_reverse", "k2rILi8ELb0", "SHFL.DOWN", 1, 1)):
+                                     ("g2_forward_x2", "k2f_x2ILi8E", "SHFL.UP", 2, 2), ("g2_reverse", "k2rILi8ELb0", "SHFL.DOWN", 1, 1),
+                                     ("g2_reverse_k3", "k2rILi3ELb0", "SHFL.DOWN", 1, 1), ("g2_reverse_x2_k3", "k2r_x2ILi3E", "SHFL.DOWN", 1, 2)):
         try:
-            doc[tag] = count(pat, 4, 8, npair, sh, per)
+            doc[tag] = count(pat, 4, 3 if tag.endswith("k3") else 8, npair, sh, per)
         except Exception as e:      # a kernel without a 128-bit store in its loop (score-only) has no such block
             doc[tag] = {"error": str(e)}
     prev = os.path.join(ROOT, "profiles", "sass_counts.json")
@@ -132,7 +133,7 @@ def main():
             pass
     os.makedirs(os.path.dirname(prev), exist_ok=True)
     json.dump(doc, open(prev, "w"), indent=1)
-    for tag in ("x2", "x1", "x2_half_k6", "g2_forward", "g2_forward_score_only", "g2_forward_x2", "g2_reverse"):
+    for tag in ("x2", "x1", "x2_half_k6", "g2_forward", "g2_forward_score_only", "g2_forward_x2", "g2_reverse", "g2_reverse_k3", "g2_reverse_x2_k3"):
         d = doc[tag]
         if "error" in d:
             print(tag, d["error"])
