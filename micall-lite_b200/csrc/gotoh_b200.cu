@@ -376,12 +376,21 @@ int launch_forward_cta(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
 int launch_forward_flow(const gotoh_b200_plan* pl, const FwdParams& fp, int ntasks) {
     const Workspace* ws = pl->ws;
     const size_t per_warp = FwdSmem<Vec32, 8>::per_warp(pl->ncls);
-    const size_t smem = per_warp * FWD_WARPS;
-    if (smem > 220 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
-    CU(cudaFuncSetAttribute(k_forward_flow<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(GOTOH_MIN_CTAS, (200 * 1024) / std::max<size_t>(smem, 1)));
-    const int grid = std::max(1, std::min((ntasks + FWD_WARPS - 1) / FWD_WARPS, ws->sm_count * ctas_per_sm));
-    GOTOH_LAUNCH((k_forward_flow<8>), dim3(grid), dim3(FWD_WARPS * 32), smem, ws->stream, fp);
+    if (per_warp * FWD_WARPS > 220 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", per_warp * FWD_WARPS);
+    CU(cudaFuncSetAttribute(k_forward_flow<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * FWD_WARPS)));
+    // The kernel is latency-bound (dependent int32 cell chain), so resident warps per SM are what counts: 16 by registers,
+    // but the per-warp query profile (1 KB per reference byte class) usually caps it lower.  Ask the runtime how many CTAs
+    // of 4, 3 or 2 warps fit and take the shape with the most warps (HCV genomes, 14 classes: 4 x 3 = 12 -> 3 x 5 = 15).
+    int warps = FWD_WARPS, ctas_per_sm = 1, best = 0;
+    for (int w = FWD_WARPS; w >= 2; --w) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_forward_flow<8>, w * 32, per_warp * w) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+        if (nb * w > best) { best = nb * w; warps = w; ctas_per_sm = nb; }
+    }
+    if (best == 0) ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(GOTOH_MIN_CTAS, (200 * 1024) / std::max<size_t>(per_warp * FWD_WARPS, 1)));
+    const size_t smem = per_warp * warps;
+    const int grid = std::max(1, std::min((ntasks + warps - 1) / warps, ws->sm_count * ctas_per_sm));
+    GOTOH_LAUNCH((k_forward_flow<8>), dim3(grid), dim3(warps * 32), smem, ws->stream, fp);
     CU(cudaGetLastError());
     return GOTOH_B200_OK;
 }
