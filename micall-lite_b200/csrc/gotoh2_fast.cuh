@@ -374,9 +374,10 @@ struct FwdX2 {
     enum { K4 = (K + 3) / 4, KMASK = (1 << K) - 1 };
     int lane, M, Na, Nb, j0, u, v, inf16, S;
     unsigned one, two, four, neg1, keep;
-    unsigned v2, negu2, c_nr, c_nn, injq, c0run, c0step;
+    unsigned v2, negu2l, c_nr, c_nn, injq, c0run, c0step;   // negu2l, c0step: LINEAR words (lo + 65536*hi), added by IMAD
     const uint4* prof_lane;
     const uint8_t* cls;
+    const uint8_t* clsl;           // cls - lane: one pointer add per block instead of per step
     unsigned vq[K];
     unsigned R[K], P[K], nRu[K];
     unsigned sendR, sendQ, Rd_in;
@@ -398,18 +399,18 @@ struct FwdX2 {
         }
         Rd_in = pk2(row0(min(j0, Na), is_global), row0(min(j0, Nb), is_global));
         bf = pk2(row0(Na, is_global), row0(Nb, is_global));
-        best_i_a = best_i_b = 0;
+        best_i_a = best_i_b = lane;                 // the STEP of row 0 (row = step - lane)
     }
 
     template <bool SLOW>
     __device__ __forceinline__ void step(const int t, const int s, const int is_global) {
         const int i = t - lane;
         const int my_cls = next_cls;
-        next_cls = cls[i];
+        next_cls = clsl[t];
         unsigned Rl = __shfl_up_sync(0xffffffffu, sendR, 1);
         unsigned Ql = __shfl_up_sync(0xffffffffu, sendQ, 1);
         unsigned rdiag = Rd_in;
-        c0run = __vadd2(c0run, c0step);                 // column 0 (_gotoh2.c:101-116), both halves alike
+        c0run = c0run * one + c0step;                   // column 0 (_gotoh2.c:101-116); both operands keep a negative low half (or are 0)
         Rl = Rl * keep + c0run;
         Ql = Ql * keep + injq;
         Rd_in = Rl;
@@ -458,14 +459,14 @@ struct FwdX2 {
             else { wlo_a.w = la; whi_a.w = ha; wlo_b.w = lb; whi_b.w = hb; }
         }
         // last column: first strict minimum scanning top-down (_gotoh2.c:330-339), per half
-        bf = __vadd2(bf, negu2);
+        bf = bf * one + negu2l;                         // bf < 0 in both halves, always: a linear add on the FMA pipe
         {
             bool keep_hi, keep_lo;                        // bf <= R: no new minimum
             const unsigned nb = __vibmin_s16x2(bf, R[K - 1], &keep_hi, &keep_lo);
             if (!SLOW || (i >= 1 && i <= M)) {
                 bf = nb;
-                if (!keep_lo) best_i_a = i;
-                if (!keep_hi) best_i_b = i;
+                if (!keep_lo) best_i_a = t;
+                if (!keep_hi) best_i_b = t;
             }
         }
         if (SLOW) {
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(128, 4) k2f_x2(const Params p) {
     w.lane = lane;
     w.u = p.u; w.v = p.v;
     w.inf16 = p.inf16; w.S = p.shift16;
-    w.v2 = pk2(p.v, p.v); w.negu2 = pk2(-p.u, -p.u);
+    w.v2 = pk2(p.v, p.v); w.negu2l = lin2(-p.u, -p.u);
     w.c_nn = 65536u;
     w.c_nr = lin2(1 - p.v, 1 - p.v) + 65536u;
     w.one = p.two >> 1; w.two = p.two; w.four = p.four; w.neg1 = p.neg1;
@@ -522,10 +523,11 @@ __global__ void __launch_bounds__(128, 4) k2f_x2(const Params p) {
         const int j0 = lane * K;
         w.M = M; w.Na = Na; w.Nb = Nb; w.j0 = j0;
         w.cls = p.s1_idx + pa.ref_pos;
+        w.clsl = w.cls - lane;
         w.row_min_a = w.row_min_b = 2147483647; w.row_j_a = w.row_j_b = 0; w.r_ll_a = w.r_ll_b = 0;
         // column 0 in the shifted frame: R'(i,0) = v - S (global) or -i*u - S (local)
         w.c0run = lane == 0 ? (p.is_global ? pk2(p.v - p.shift16, p.v - p.shift16) : pk2(-p.shift16, -p.shift16)) : 0u;
-        w.c0step = (lane == 0 && !p.is_global) ? pk2(-p.u, -p.u) : 0u;
+        w.c0step = (lane == 0 && !p.is_global) ? lin2(-p.u, -p.u) : 0u;
 
         __syncwarp();
 #pragma unroll
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(128, 4) k2f_x2(const Params p) {
             const int owner = ((N - 1) / K) & 31;
             int col_min = (half ? hi16(w.bf) : lo16(w.bf)) + (i_fin + N) * p.u + p.shift16;
             col_min = __shfl_sync(0xffffffffu, col_min, owner);
-            const int col_i = __shfl_sync(0xffffffffu, half ? w.best_i_b : w.best_i_a, owner);
+            const int col_i = __shfl_sync(0xffffffffu, (half ? w.best_i_b : w.best_i_a) - lane, owner);
             const int r_ll = __shfl_sync(0xffffffffu, half ? w.r_ll_b : w.r_ll_a, owner);
             if (lane == 0) {
                 int best = r_ll, bi = M, bj = N;

@@ -235,6 +235,7 @@ struct Wave {
     unsigned four, one;                 // == 4 at run time; opaque to ptxas so acc*four+x stays an IMAD (FMA pipe)
     const uint4* prof_lane;        // prof + lane
     const uint8_t* cls;            // cls[i-1] = class of reference row i
+    const uint8_t* clsl;           // cls - lane: clsl[t] is the class of row t - lane + 1 (one add per block, not per step)
     int2* ring;
     const int2* bnd_in;
     int2* bnd_out;
@@ -266,7 +267,7 @@ struct Wave {
     T Sd_in;                       // S^(i-1, j0): diagonal input of column j0+1
     T diag0;                       // lane 0 / strip 0: "S(i-1,0) = 0" (gotoh.cpp:292) in the stored frame
     T best;                        // last column: running max in the stored frame of the current row
-    int best_i_a, best_i_b;        //              and its row (largest i wins ties, gotoh.cpp:406-410)
+    int best_i_a, best_i_b;        //              and the STEP t of its row i = t - lane (largest i wins ties, gotoh.cpp:406-410)
     int lr_best_a, lr_j_a, lr_best_b, lr_j_b;   // last row (largest j wins ties, gotoh.cpp:399-403)
     int next_cls;
     uint4 dwords;
@@ -285,9 +286,9 @@ struct Wave {
         // seed below any reachable score, expressed in the row-0 frame of column N
         // (Vec16: every stored value of an admitted pair is >= 0 after the shift, so -4 is below all of them and, unlike
         // the plan-wide bound smin_m1, always fits 16 bits)
-        if (NP == 2) best = V::pack(Na * g4 - 4, Nb * g4 - 4);
+        if (NP == 2) best = V::pack(Na * g4, Nb * g4);          // = a stored 0 carried to column N: real values win ties
         else best = V::pack(4 * smin_m1 + Na * g4, 4 * smin_m1 + Nb * g4);
-        best_i_a = best_i_b = 0;
+        best_i_a = best_i_b = lane;                              // row 0
     }
 
     // One lane-step: K cells of row i = t - lane.  SLOW adds the rarely needed per-lane checks
@@ -297,7 +298,7 @@ struct Wave {
     __device__ __forceinline__ void step(const int t, const int s) {
         const int i = t - lane;
         const int my_cls = next_cls;
-        next_cls = cls[i];                                  // class of row i+1 (padded on both sides)
+        next_cls = clsl[t];                                 // class of row i+1 (padded on both sides)
 
         // ---- hand-off from the left neighbour (its row i, produced last step) ---------------
         T Sl = __shfl_up_sync(0xffffffffu, sendS, 1);
@@ -396,7 +397,7 @@ struct Wave {
         }
         sendS = S[K - 1];
         sendQ = q;
-        if (!MULTI || strip == 0) diag0 = V::add(diag0, c_g4_lane0);
+        if (!MULTI || strip == 0) diag0 = V::addlin(diag0, one, c_g4_lane0);   // >= 0 in the shifted frame: an IMAD
 
         // ---- directions: 2K bits per alignment per lane-step -------------------------------------
         const unsigned dstep = accC - accS;
@@ -414,13 +415,13 @@ struct Wave {
         // ---- last column: running max, ties -> larger i (gotoh.cpp:406-410) -----------------------
         // Tracked in the stored frame of the current row: carrying a score one row down adds 4g.
         if (!MULTI || last_strip) {
-            best = V::add(best, c_g4);
+            best = V::addlin(best, one, c_g4);                 // best >= 0 (shifted frame): FMA pipe instead of VIADD.16x2
             bool pa, pb;
             const T nb = V::bmax(S[K - 1], best, &pa, &pb);
             if (!SLOW || i <= M) {
                 best = nb;
-                if (pa) best_i_a = i;
-                if (NP == 2) { if (pb) best_i_b = i; }
+                if (pa) best_i_a = t;
+                if (NP == 2) { if (pb) best_i_b = t; }
             }
         }
         // ---- boundary column for the next strip --------------------------------------------------
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
         int2* bnd0 = MULTI ? p.bnd + ((int64_t)(blockIdx.x * (blockDim.x >> 5) + warp) * 2) * p.bnd_stride : nullptr;
         w.M = M; w.Na = Na; w.Nb = Nb;
         w.cls = p.ref_cls + pa.ref_pos;
+        w.clsl = w.cls - lane;
         w.lr_best_a = w.lr_best_b = -2147483647;
         w.lr_j_a = w.lr_j_b = 0;
 
@@ -664,9 +666,9 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
             int best_a = ((V::lo(w.best) - w.z4) >> 2) - (roff + Na) * p.gep;
             int best_b = ((V::hi(w.best) - w.z4) >> 2) - (roff + Nb) * p.gep;
             best_a = __shfl_sync(0xffffffffu, best_a, la);
-            const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a, la);
+            const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a - lane, la);
             best_b = __shfl_sync(0xffffffffu, best_b, lb & 31);
-            const int bi_b = __shfl_sync(0xffffffffu, w.best_i_b, lb & 31);
+            const int bi_b = __shfl_sync(0xffffffffu, w.best_i_b - lane, lb & 31);
             if (lane == 0) {
                 // strict '>' : the last row only wins when it is strictly better (gotoh.cpp:429)
                 if (lr_best_a > best_a) { p.score[task.pair_a] = lr_best_a; p.end_i[task.pair_a] = M; p.end_j[task.pair_a] = lr_j_a; }
@@ -731,6 +733,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_flow
         const int j0 = (strip * 32 + lane) * K;
         w.M = M; w.Na = Na; w.Nb = Na;
         w.cls = p.ref_cls + pa.ref_pos;
+        w.clsl = w.cls - lane;
         w.lr_best_a = w.lr_best_b = -2147483647;
         w.lr_j_a = w.lr_j_b = 0;
         w.strip = strip;
@@ -810,7 +813,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_flow
             const int la = (Na - 1) / K - (nstrips - 1) * 32;
             int best_a = (V::lo(w.best) >> 2) - (i_fin + Na) * p.gep;
             best_a = __shfl_sync(0xffffffffu, best_a, la);
-            const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a, la);
+            const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a - lane, la);
             if (lane == 0) {
                 if (lr_best > best_a) { p.score[task.pair_a] = lr_best; p.end_i[task.pair_a] = M; p.end_j[task.pair_a] = lr_j; }
                 else { p.score[task.pair_a] = best_a; p.end_i[task.pair_a] = bi_a; p.end_j[task.pair_a] = Na; }
@@ -887,10 +890,11 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_cta(
         const uint8_t* qa = p.qry + pa.qry_pos;
         w.M = M; w.Na = Na; w.Nb = Na;
         w.cls = p.ref_cls + pa.ref_pos;
+        w.clsl = w.cls - lane;
         w.lr_best_a = w.lr_best_b = -2147483647;
         w.lr_j_a = w.lr_j_b = 0;
         w.best = V::both(0);
-        w.best_i_a = w.best_i_b = 0;
+        w.best_i_a = w.best_i_b = lane;
 
         for (int strip = warp; strip < nstrips; strip += FWD_WARPS) {
             const int j0 = (strip * 32 + lane) * K;
@@ -964,7 +968,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_cta(
             const int la = (Na - 1) / K - (nstrips - 1) * 32;
             int best_a = (V::lo(w.best) >> 2) - (i_fin + Na) * p.gep;
             best_a = __shfl_sync(0xffffffffu, best_a, la);
-            const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a, la);
+            const int bi_a = __shfl_sync(0xffffffffu, w.best_i_a - lane, la);
             if (lane == 0) {
                 if (lr_best > best_a) { p.score[task.pair_a] = lr_best; p.end_i[task.pair_a] = M; p.end_j[task.pair_a] = lr_j; }
                 else { p.score[task.pair_a] = best_a; p.end_i[task.pair_a] = bi_a; p.end_j[task.pair_a] = Na; }
