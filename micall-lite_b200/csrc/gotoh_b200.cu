@@ -1062,6 +1062,8 @@ enum { NWS = 8, NBUILD = 4 };
 struct DeviceCtx {
     std::mutex mu;
     Workspace ws[NWS];
+    int64_t free_plus_cached = 0;   // device memory available to the workspaces, measured on the first call (cudaMemGetInfo
+                                    // now and then takes tens of ms; gotoh_b200_release_cache resets it)
 };
 std::mutex g_ctx_mu;
 DeviceCtx* g_ctx[64] = {nullptr};
@@ -1090,12 +1092,18 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     nws = std::max(1, std::min(nws, (int)NWS));
     for (int w = 0; w < nws; ++w) { const int rc = ctx->ws[w].init(dev); if (rc) return rc; }
     CU(cudaSetDevice(dev));
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    int64_t cached = 0;
-    for (int w = 0; w < NWS; ++w) cached += (int64_t)ctx->ws[w].d_dir.cap * 16;
+    {
+        // re-measured until the workspaces hold their arenas; after that a call needs no new device memory
+        int64_t cached = 0;
+        for (int w = 0; w < NWS; ++w) cached += (int64_t)ctx->ws[w].d_dir.cap * 16;
+        if (ctx->free_plus_cached <= 0 || cached == 0) {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            ctx->free_plus_cached = (int64_t)free_b + cached;
+        }
+    }
     // small slabs keep the pipeline's fill and drain short (first packing, last D2H); 3 GB of arena = ~16 k reads
-    int64_t slab_budget = std::min<int64_t>(((int64_t)free_b + cached) / (nws + 2), (int64_t)3 << 30);
+    int64_t slab_budget = std::min<int64_t>(ctx->free_plus_cached / (nws + 2), (int64_t)3 << 30);
     slab_budget = std::max<int64_t>(slab_budget, (int64_t)256 << 20);
     if (getenv("GOTOH_B200_SLAB_MB")) slab_budget = (int64_t)atoll(getenv("GOTOH_B200_SLAB_MB")) << 20;   // tests
     gotoh_b200_plan plans[NWS];
@@ -1291,6 +1299,7 @@ extern "C" void gotoh_b200_release_cache(void) {
         if (g_ctx[d]) {
             std::lock_guard<std::mutex> lk2(g_ctx[d]->mu);
             for (int w = 0; w < NWS; ++w) g_ctx[d]->ws[w].release();
+            g_ctx[d]->free_plus_cached = 0;
         }
 }
 
