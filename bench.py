@@ -287,7 +287,8 @@ def run_ours(args, rank, world, local_rank):
     roof_gcups = min(roof_alu, roof_issue)
     dir_bytes = 0.25 * cells * (1.03)                 # 2 bits/cell + wavefront fill/drain slots
     roofline = {
-        "bound": "int_alu", "kernel": "k_forward<%s,8,false>" % ("Vec16" if use_x2 else "Vec32"),
+        # integer roofline (north_star): which of its two terms binds - the ALU pipe or the ALU+FMA issue slots
+        "bound": "int_alu" if roof_alu <= roof_issue else "int_issue", "kernel": "k_forward<%s,8,false>" % ("Vec16" if use_x2 else "Vec32"),
         "achieved": fwd_gcups, "peak": roof_gcups, "unit": "GCUPS", "frac": (fwd_gcups / roof_gcups) if fwd_gcups else None,
         "peak_def": "min(measured ALU-pipe rate %.0f G instr/s / %.2f ALU instr per cell, measured ALU+FMA issue rate %.0f / %.2f instr per cell); "
                     "rates from gotoh_b200_int_peak in this run, counts from cuobjdump (profiles/sass_counts.json)" % (alu_rate, alu_per_cell, issue_rate, instr_per_cell),
