@@ -143,6 +143,19 @@ def test_emu_half_warp_wavefronts(emu_aligner, oracle_port, monkeypatch):
         assert g == oracle_port.align_it(ref[200:900], q, 10, 3, 1)
 
 
+def test_emu_many_tiny_pairs_take_the_radix_sorted_task_order(emu_aligner, oracle_port):
+    """More than 2048 int16x2-eligible pairs in one plan: the host orders the task keys with its radix sort (smaller
+    plans use std::sort), couples partners that share a reference and forms half-warp quads; tiny grids keep the
+    emulator fast."""
+    rng = random.Random(77)
+    refs = ["".join(rng.choice("ACGT") for _ in range(rng.randint(4, 14))) for _ in range(9)]
+    ridx = [rng.randrange(len(refs)) for _ in range(2600)]
+    qs = ["".join(rng.choice("ACGTN") for _ in range(rng.randint(1, 12))) for _ in ridx]
+    got = emu_aligner.align_batch(refs, qs, 10, 3, 1, 0, ref_idx=ridx)
+    for k, (r, q) in enumerate(zip(ridx, qs)):
+        assert got[k] == oracle_port.align_it(refs[r], q, 10, 3, 1), (refs[r], q)
+
+
 def test_emu_many_reference_byte_classes(emu_aligner, oracle_port):
     """A reference using ~120 distinct bytes needs a 120-class query profile: the launcher drops to
     fewer warps per CTA instead of failing."""
