@@ -532,6 +532,13 @@ __global__ void __launch_bounds__(128, 4) k2f_x2(const Params p) {
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < K; ++k) w.vq[k] = pk2((j0 + k) < Na ? p.v : 0, (j0 + k) < Nb ? p.v : 0);
+        // alphabet indices of this lane's columns, read once (-1: padding column), then one table load per class
+        int xa[K], xb[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            xa[k] = (j0 + k) < Na ? (int)sa[j0 + k] : -1;
+            xb[k] = (j0 + k) < Nb ? (int)sb[j0 + k] : -1;
+        }
         for (int c = 0; c < p.l; ++c) {
             const int32_t* drow = p.dmat + c * p.l;
 #pragma unroll
@@ -539,10 +546,12 @@ __global__ void __launch_bounds__(128, 4) k2f_x2(const Params p) {
                 unsigned e[4];
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const int k = kq * 4 + kk, ja = j0 + k;
+                    const int k = kq * 4 + kk;
                     int ea = e_pad, eb = e_pad;
-                    if (k < K && ja < Na) ea = -drow[sa[ja]] - 2 * p.u;
-                    if (k < K && ja < Nb) eb = -drow[sb[ja]] - 2 * p.u;
+                    if (k < K) {
+                        if (xa[k] >= 0) ea = -drow[xa[k]] - 2 * p.u;
+                        if (xb[k] >= 0) eb = -drow[xb[k]] - 2 * p.u;
+                    }
                     e[kk] = lin2(ea, eb);
                 }
                 prof[(c * K4 + kq) * 32 + lane] = make_uint4(e[0], e[1], e[2], e[3]);
