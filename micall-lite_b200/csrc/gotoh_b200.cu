@@ -1102,8 +1102,9 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
             ctx->free_plus_cached = (int64_t)free_b + cached;
         }
     }
-    // small slabs keep the pipeline's fill and drain short (first packing, last D2H); 3 GB of arena = ~16 k reads
-    int64_t slab_budget = std::min<int64_t>(ctx->free_plus_cached / (nws + 2), (int64_t)3 << 30);
+    // small slabs keep the pipeline's fill and drain short (first packing, last D2H); 1.5 GB of arena = ~8 k reads.  (With
+    // the cheaper host packing and the FIFO of forward kernels, 1-1.5 GB measured ~6 % faster end to end than 3 GB on B200.)
+    int64_t slab_budget = std::min<int64_t>(ctx->free_plus_cached / (nws + 2), (int64_t)1536 << 20);
     slab_budget = std::max<int64_t>(slab_budget, (int64_t)256 << 20);
     if (getenv("GOTOH_B200_SLAB_MB")) slab_budget = (int64_t)atoll(getenv("GOTOH_B200_SLAB_MB")) << 20;   // tests
     gotoh_b200_plan plans[NWS];
