@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GOTOH_B200_VERSION 100 /* 0.1.0 */
+#define GOTOH_B200_VERSION 200 /* 0.2.0 */
 
 /* matrix_id: which of the reference's table initialisers applies (gotoh.cpp:26-213). */
 enum {
@@ -49,8 +49,10 @@ enum {
     GOTOH_B200_ENODEVICE = -6, /* no usable CUDA device / device index not present */
     GOTOH_B200_ECUDA = -7,     /* CUDA runtime error (message in gotoh_b200_last_error) */
     GOTOH_B200_ENOMEM = -8,    /* host or device allocation failed */
-    GOTOH_B200_ETRACEBACK = -9 /* gotoh2 only: no a/b/c bit set on the path, "Traceback failed, try local
+    GOTOH_B200_ETRACEBACK = -9, /* gotoh2 only: no a/b/c bit set on the path, "Traceback failed, try local
                                   alignment" (_gotoh2.c:403-407,601-603); that pair's score is INT32_MIN */
+    GOTOH_B200_ECAPACITY = -10 /* tight / compact result forms: the caller's output buffer is too small for the
+                                  results; gotoh_b200_last_error() names the size that is needed */
 };
 
 /* Library / device info. */
@@ -90,6 +92,62 @@ int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_t* ref_off,
                                int32_t gip, int32_t gep, int32_t use_terminal, int32_t matrix_id,
                                uint8_t* out_ref, uint8_t* out_qry, const int64_t* out_off,
                                int32_t* out_len, int32_t* out_score, uint32_t device_mask);
+
+/*
+ * On a non-zero return of any batched entry point the contents of the caller's output buffers are unspecified
+ * (slabs that were finished before the failure was detected may already have been copied back).
+ *
+ * Tight form of gotoh_b200_align_batch: the same results, but the library chooses the layout - pair k's two aligned
+ * strings start at out_off[k] (an OUTPUT, n_pairs entries) and are out_len[k] bytes long, pairs follow each other
+ * without stride tails, so only bytes that carry results cross PCIe (the strided form ships the zero tail between
+ * out_len and the M+N stride: 7.6 % of the bytes on 251-nt reads).  out_cap = bytes available in EACH of out_ref /
+ * out_qry; sum of (len(standard)+len(seq)) over the pairs always suffices (GOTOH_B200_ECAPACITY otherwise).  With
+ * several devices in device_mask each device fills its own slice of the capacity, so out_off is increasing but not
+ * gap-free across device boundaries.
+ */
+int32_t gotoh_b200_align_batch_tight(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
+                                     const int32_t* ref_idx,
+                                     const uint8_t* qry_bytes, const int64_t* qry_off, int64_t n_pairs,
+                                     int32_t gip, int32_t gep, int32_t use_terminal, int32_t matrix_id,
+                                     uint8_t* out_ref, uint8_t* out_qry, int64_t out_cap, int64_t* out_off,
+                                     int32_t* out_len, int32_t* out_score, uint32_t device_mask);
+
+/*
+ * Compact form: the alignment itself instead of its rendering.  The reference returns two strings of length ~M+N per
+ * pair (gotoh.cpp:436-513, Py_BuildValue("ssi") :650) - for a 251-nt read against a 3039-nt standard 6.6 KB of which
+ * 92 % is the standard's overhang against '-'.  This entry point returns, per pair k, one record of 8 int32
+ *     out_rec[8k + GOTOH_B200_REC_*]:  SCORE (3rd value of align_it), OUT_LEN (length of either aligned string),
+ *         I0, J0   cell where the traceback stopped (gotoh.cpp:452 loop exit; one of them is 0): the left overhang is
+ *                  standard[0..I0) against '-' or seq[0..J0) against '-'                       (gotoh.cpp:489-496)
+ *         END_I, END_J  end cell chosen at gotoh.cpp:418-450: the right overhang is seq[END_J..N) against '-' when
+ *                  END_I == M and END_J < N, else standard[END_I..M) against '-'
+ *         N_OPS    traceback steps between them, M_N = (M << 16 | N) when both trimmed lengths are < 65536, else -1
+ * and the op script: op t (t = 0 .. N_OPS-1, counted from the END cell backwards, exactly the order of the reference's
+ * traceback loop gotoh.cpp:452-487) is bits [2(t&15)+1 : 2(t&15)] of word out_ops[out_ops_off[k] + (t>>4)]:
+ *     0 diagonal (one character of each), 1 up (a standard character against '-'), 2 left ('-' against a seq character).
+ * (standard, seq are the TRIMMED - AA_RB: and degapped - inputs.)  The two strings of align_it are a pure function of
+ * the inputs and this record (gotoh_b200/compact.py expands them on demand; tests compare with the string entry point
+ * and the oracle byte for byte).  out_ops_cap = capacity of out_ops in 32-bit words; sum of ceil((M+N)/16) always
+ * suffices, real alignments need ~ceil(min(M,N)/16)+1 per pair (GOTOH_B200_ECAPACITY names the need).  out_ops_off has
+ * n_pairs entries (OUTPUT).  ~100 B per 251-nt read cross PCIe instead of 6.6 KB.
+ */
+enum { GOTOH_B200_REC_SCORE = 0, GOTOH_B200_REC_OUT_LEN = 1, GOTOH_B200_REC_I0 = 2, GOTOH_B200_REC_J0 = 3,
+       GOTOH_B200_REC_END_I = 4, GOTOH_B200_REC_END_J = 5, GOTOH_B200_REC_N_OPS = 6, GOTOH_B200_REC_M_N = 7,
+       GOTOH_B200_REC_WORDS = 8 };
+int32_t gotoh_b200_align_batch_compact(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
+                                       const int32_t* ref_idx,
+                                       const uint8_t* qry_bytes, const int64_t* qry_off, int64_t n_pairs,
+                                       int32_t gip, int32_t gep, int32_t use_terminal, int32_t matrix_id,
+                                       int32_t* out_rec, uint32_t* out_ops, int64_t out_ops_cap,
+                                       int64_t* out_ops_off, uint32_t device_mask);
+
+/*
+ * Host-ceiling probe for the result copy (bench.py: e2e.host_ceiling): `reps` plain cudaMemcpyAsync device-to-host
+ * copies of `bytes` from a scratch device buffer on `device` into host_buf (pinned memory from gotoh_b200_host_alloc
+ * for the full rate), timed with CUDA events; *seconds = time of all reps.  Run on every rank at once it measures what
+ * the box can absorb, which is what bounds the string forms on multi-GPU hosts.
+ */
+int32_t gotoh_b200_d2h_probe(int32_t device, void* host_buf, int64_t bytes, int32_t reps, double* seconds);
 
 /*
  * Staged form of the same call, for callers that keep data resident in HBM or want the

@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = [nvcc_path()] + NVCC_FLAGS + [os.path.join(HERE, s) for s in SOURCES] + ["-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    log = os.path.join(PKG, "lib", "ptxas.log")
+    log = os.path.join(PKG, "lib", "ptxas.log")      # register / spill report of this build (git-ignored, like the .so)
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:

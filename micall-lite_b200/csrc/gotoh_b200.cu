@@ -140,6 +140,12 @@ struct Workspace {
     DevBuf<int32_t> d_flow;         // [3][slots]: progress, last-row partial score, its column
     PinBuf<Task> h_stasks;
     DevBuf<uint32_t> d_ops, d_counter;
+    // tight / compact result forms: caller-order result sizes, their prefix sums, compact records and packed op scripts
+    DevBuf<int32_t> d_scan_in, d_rec;
+    DevBuf<int64_t> d_scan_out;
+    DevBuf<uint32_t> d_cops;
+    PinBuf<int64_t> h_total;        // the slab's total (bytes / words), copied back with the per-pair arrays (phase A)
+    cudaEvent_t ev_a = 0;           // recorded after phase A: the host may read h_total and enqueue the result copy (phase B)
     // pinned staging
     PinBuf<uint8_t> h_ref_raw, h_ref_cls, h_qry;
     PinBuf<PairInfo> h_pairs;
@@ -156,6 +162,8 @@ struct Workspace {
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&ev[i]));
         CU(cudaEventCreateWithFlags(&ev_fwd, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
+        CU(h_total.ensure(8));
         ready = true;
         return GOTOH_B200_OK;
     }
@@ -168,6 +176,8 @@ struct Workspace {
         d_end_j.release(); d_nops.release(); d_i0.release(); d_j0.release(); d_len_plan.release();
         d_out_len.release(); d_out_score.release(); d_dir.release(); d_bnd.release(); d_stasks.release(); d_flow.release(); h_stasks.release(); d_ops.release();
         d_counter.release();
+        d_scan_in.release(); d_rec.release(); d_scan_out.release(); d_cops.release(); h_total.release();
+        if (ev_a) { cudaEventDestroy(ev_a); ev_a = 0; }
         h_ref_raw.release(); h_ref_cls.release(); h_qry.release(); h_pairs.release(); h_tasks.release(); h_table4.release();
         for (int i = 0; i < 4; ++i) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = 0; }
         if (ev_fwd) { cudaEventDestroy(ev_fwd); ev_fwd = 0; }
@@ -194,8 +204,12 @@ struct Chunk {
 
 }  // namespace
 
+enum { OUT_STRIDED = 0, OUT_TIGHT = 1, OUT_COMPACT = 2 };   // result forms (include/gotoh_b200.h)
+
 struct gotoh_b200_plan {
     Workspace* ws = nullptr;
+    int out_mode = OUT_STRIDED;
+    int64_t ops_words = 0;                 // op-script words of all pairs (capacity of d_ops / d_cops)
     bool owns_ws = false;
     int64_t n_pairs = 0;
     int gip = 0, gep = 0, term = 1, matrix = 0;
@@ -555,7 +569,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
             // uninitialised end indices
             const long long worst = 2LL * pl->gip + ((long long)std::max(h.M, h.N) + 1) * pl->gep;
             if (worst >= 100000) { if (!te.code) { te.code = GOTOH_B200_ESENTINEL; te.pair = k; } return; }
-            if (out_off[k + 1] - out_off[k] < (int64_t)h.M + h.N || out_off[k + 1] - out_off[k] > 0x7fffffffLL) {
+            if (out_off && (out_off[k + 1] - out_off[k] < (int64_t)h.M + h.N || out_off[k + 1] - out_off[k] > 0x7fffffffLL)) {
                 if (!te.code) { te.code = GOTOH_B200_ERANGE; te.pair = k; te.byte = -1; }
                 return;
             }
@@ -720,8 +734,9 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         memset(&pi, 0, sizeof(pi));
         pi.ref_pos = ref_pos[(size_t)h.ref];
         pi.qry_pos = h.qpos;
-        pi.out_off = out_off[pair_begin + h.orig] - out_off[pair_begin];
-        pi.out_cap = (int32_t)(out_off[pair_begin + h.orig + 1] - out_off[pair_begin + h.orig]);
+        // (tight / compact forms have no caller offsets: k_scan assigns them on the device)
+        pi.out_off = out_off ? out_off[pair_begin + h.orig] - out_off[pair_begin] : 0;
+        pi.out_cap = out_off ? (int32_t)(out_off[pair_begin + h.orig + 1] - out_off[pair_begin + h.orig]) : h.M + h.N;
         pi.M = h.M; pi.N = h.N;
         pi.K = (int16_t)K; pi.x2 = (int8_t)x2; pi.half = (int8_t)half;
         pi.orig = h.orig;
@@ -779,8 +794,12 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         pl->pairs_x1 += 1;
     }
 
-    pl->out_base = out_off[pair_begin];
-    pl->out_bytes = out_off[pair_end] - out_off[pair_begin];
+    if (out_off) { pl->out_base = out_off[pair_begin]; pl->out_bytes = out_off[pair_end] - out_off[pair_begin]; }
+    else {
+        pl->out_base = 0; pl->out_bytes = 0;
+        for (const HostPair& h : hp) pl->out_bytes += (int64_t)h.M + h.N;      // tight form: worst case of the slab
+    }
+    pl->ops_words = ops_words;
     pl->pair_base = pair_begin;
     pl->n_pairs = n;
 
@@ -796,8 +815,18 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     CU(ws->d_nops.ensure((size_t)n)); CU(ws->d_i0.ensure((size_t)n)); CU(ws->d_j0.ensure((size_t)n));
     CU(ws->d_len_plan.ensure((size_t)n)); CU(ws->d_out_len.ensure((size_t)n)); CU(ws->d_out_score.ensure((size_t)n));
     CU(ws->d_ops.ensure((size_t)ops_words));
-    CU(ws->d_out_ref.ensure((size_t)pl->out_bytes));
-    CU(ws->d_out_qry.ensure((size_t)pl->out_bytes));
+    if (pl->out_mode != OUT_COMPACT) {
+        CU(ws->d_out_ref.ensure((size_t)pl->out_bytes));
+        CU(ws->d_out_qry.ensure((size_t)pl->out_bytes));
+    }
+    if (pl->out_mode != OUT_STRIDED) {
+        CU(ws->d_scan_in.ensure((size_t)n));
+        CU(ws->d_scan_out.ensure((size_t)n + 1));
+    }
+    if (pl->out_mode == OUT_COMPACT) {
+        CU(ws->d_rec.ensure((size_t)n * 8));
+        CU(ws->d_cops.ensure((size_t)ops_words));
+    }
 
     // ---- arena budget and chunking ----------------------------------------------------------------
     int64_t biggest = 0, total_arena = 0;
@@ -931,6 +960,22 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     return GOTOH_B200_OK;
 }
 
+int launch_emit(const gotoh_b200_plan* pl, int pair_first, int pair_count, const int64_t* tight_off) {
+    const Workspace* ws = pl->ws;
+    EmitParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.pairs = ws->d_pairs.p; ep.pair_first = pair_first; ep.pair_count = pair_count;
+    ep.ref_raw = ws->d_ref_raw.p; ep.qry = ws->d_qry.p; ep.ops = ws->d_ops.p; ep.nops = ws->d_nops.p;
+    ep.i0 = ws->d_i0.p; ep.j0 = ws->d_j0.p; ep.end_i = ws->d_end_i.p; ep.end_j = ws->d_end_j.p;
+    ep.out_len_plan = ws->d_len_plan.p; ep.score_plan = ws->d_score.p;
+    ep.out_ref = ws->d_out_ref.p; ep.out_qry = ws->d_out_qry.p;
+    ep.out_len = ws->d_out_len.p; ep.out_score = ws->d_out_score.p;
+    ep.tight_off = tight_off;
+    GOTOH_LAUNCH(k_emit, dim3((pair_count + 3) / 4), dim3(128), 0, ws->stream, ep);
+    CU(cudaGetLastError());
+    return GOTOH_B200_OK;
+}
+
 // Enqueue forward DP + traceback + emit for every chunk.  With `timed`, CUDA events bracket the
 // whole run (and each chunk's forward launches) and the call synchronises; otherwise it only enqueues.
 int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_ms) {
@@ -1000,23 +1045,39 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
         wp.end_i = ws->d_end_i.p; wp.end_j = ws->d_end_j.p; wp.score = ws->d_score.p;
         wp.ops = ws->d_ops.p; wp.nops = ws->d_nops.p; wp.i0 = ws->d_i0.p; wp.j0 = ws->d_j0.p;
         wp.out_len = ws->d_len_plan.p; wp.gip = pl->gip; wp.gep = pl->gep; wp.term = pl->term;
+        wp.scan_in = pl->out_mode != OUT_STRIDED ? ws->d_scan_in.p : nullptr;
+        wp.scan_words = pl->out_mode == OUT_COMPACT ? 1 : 0;
         GOTOH_LAUNCH(k_walk, dim3((c.pair_count + 127) / 128), dim3(128), 0, ws->stream, wp);
         CU(cudaGetLastError());
-        EmitParams ep;
-        memset(&ep, 0, sizeof(ep));
-        ep.pairs = ws->d_pairs.p; ep.pair_first = c.pair_first; ep.pair_count = c.pair_count;
-        ep.ref_raw = ws->d_ref_raw.p; ep.qry = ws->d_qry.p; ep.ops = ws->d_ops.p; ep.nops = ws->d_nops.p;
-        ep.i0 = ws->d_i0.p; ep.j0 = ws->d_j0.p; ep.end_i = ws->d_end_i.p; ep.end_j = ws->d_end_j.p;
-        ep.out_len_plan = ws->d_len_plan.p; ep.score_plan = ws->d_score.p;
-        ep.out_ref = ws->d_out_ref.p; ep.out_qry = ws->d_out_qry.p;
-        ep.out_len = ws->d_out_len.p; ep.out_score = ws->d_out_score.p;
-        GOTOH_LAUNCH(k_emit, dim3((c.pair_count + 3) / 4), dim3(128), 0, ws->stream, ep);
-        CU(cudaGetLastError());
+        // strided form: this chunk's strings at the caller's offsets.  The tight / compact forms need every pair's
+        // size first (k_scan below), so their emit / pack kernel runs once, after the last chunk.
+        if (pl->out_mode == OUT_STRIDED) {
+            const int rc = launch_emit(pl, c.pair_first, c.pair_count, nullptr);
+            if (rc) return rc;
+        }
         if (timed && forward_ms) {
             CU(cudaEventSynchronize(ws->ev[3]));
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, ws->ev[2], ws->ev[3]));
             fwd_total += ms;
+        }
+    }
+    if (pl->out_mode != OUT_STRIDED && pl->n_pairs > 0) {
+        const int n = (int)pl->n_pairs;
+        GOTOH_LAUNCH(k_scan, dim3(1), dim3(SCAN_THREADS), 0, ws->stream, ws->d_scan_in.p, ws->d_scan_out.p, n);
+        CU(cudaGetLastError());
+        if (pl->out_mode == OUT_TIGHT) {
+            const int rc = launch_emit(pl, 0, n, ws->d_scan_out.p);
+            if (rc) return rc;
+        } else {
+            PackParams pp;
+            memset(&pp, 0, sizeof(pp));
+            pp.pairs = ws->d_pairs.p; pp.pair_count = n; pp.ops = ws->d_ops.p; pp.nops = ws->d_nops.p;
+            pp.i0 = ws->d_i0.p; pp.j0 = ws->d_j0.p; pp.end_i = ws->d_end_i.p; pp.end_j = ws->d_end_j.p;
+            pp.out_len_plan = ws->d_len_plan.p; pp.score_plan = ws->d_score.p;
+            pp.off = ws->d_scan_out.p; pp.rec = ws->d_rec.p; pp.cops = ws->d_cops.p;
+            GOTOH_LAUNCH(k_pack_ops, dim3((n + 3) / 4), dim3(128), 0, ws->stream, pp);
+            CU(cudaGetLastError());
         }
     }
     if (timed) {
@@ -1044,10 +1105,69 @@ int plan_fetch(gotoh_b200_plan* pl, uint8_t* out_ref, uint8_t* out_qry, int32_t*
     return GOTOH_B200_OK;
 }
 
+// What a call writes into: the caller's result buffers of one of the three result forms (include/gotoh_b200.h).
+struct OutSpec {
+    int mode = OUT_STRIDED;
+    uint8_t* out_ref = nullptr;          // strided, tight
+    uint8_t* out_qry = nullptr;
+    const int64_t* out_off_in = nullptr; // strided: caller's offsets (n+1)
+    int64_t* out_off = nullptr;          // tight: byte offsets per pair; compact: op-script word offsets per pair (OUTPUT, n)
+    int32_t* out_len = nullptr;          // strided, tight
+    int32_t* out_score = nullptr;
+    int32_t* out_rec = nullptr;          // compact: 8 words per pair
+    uint32_t* out_ops = nullptr;
+    int64_t cap_lo = 0, cap_hi = 0;      // tight / compact: this device's slice of the caller's capacity (bytes / words)
+};
+
+// Tight / compact forms, phase A: the per-pair arrays and the slab's total size; the event tells the host when it may
+// read the total and enqueue phase B (the result bytes themselves, whose count and position it only knows then).
+int plan_fetch_a(gotoh_b200_plan* pl, const OutSpec& o) {
+    Workspace* ws = pl->ws;
+    pl->d2h_bytes = 0;
+    auto d2h = [&](void* h, const void* d, size_t bytes) -> cudaError_t {
+        pl->d2h_bytes += (int64_t)bytes;
+        return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ws->stream);
+    };
+    if (o.mode == OUT_TIGHT) {
+        CU(d2h(o.out_len + pl->pair_base, ws->d_out_len.p, (size_t)pl->n_pairs * sizeof(int32_t)));
+        CU(d2h(o.out_score + pl->pair_base, ws->d_out_score.p, (size_t)pl->n_pairs * sizeof(int32_t)));
+    } else {
+        CU(d2h(o.out_rec + pl->pair_base * 8, ws->d_rec.p, (size_t)pl->n_pairs * 8 * sizeof(int32_t)));
+    }
+    CU(d2h(ws->h_total.p, ws->d_scan_out.p + pl->n_pairs, sizeof(int64_t)));
+    CU(cudaEventRecord(ws->ev_a, ws->stream));
+    return GOTOH_B200_OK;
+}
+
+// Phase B: the slab's result bytes, tightly packed, to position `base` of the caller's buffer; per-pair offsets are
+// the running sum of the sizes phase A brought back.
+int plan_fetch_b(gotoh_b200_plan* pl, const OutSpec& o, int64_t base, int64_t total) {
+    Workspace* ws = pl->ws;
+    if (o.mode == OUT_TIGHT) {
+        if (total > 0) {
+            CU(cudaMemcpyAsync(o.out_ref + base, ws->d_out_ref.p, (size_t)total, cudaMemcpyDeviceToHost, ws->stream));
+            CU(cudaMemcpyAsync(o.out_qry + base, ws->d_out_qry.p, (size_t)total, cudaMemcpyDeviceToHost, ws->stream));
+        }
+        pl->d2h_bytes += 2 * total;
+        int64_t run = base;
+        const int32_t* len = o.out_len + pl->pair_base;
+        int64_t* off = o.out_off + pl->pair_base;
+        for (int64_t k = 0; k < pl->n_pairs; ++k) { off[k] = run; run += len[k]; }
+    } else {
+        if (total > 0) CU(cudaMemcpyAsync(o.out_ops + base, ws->d_cops.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ws->stream));
+        pl->d2h_bytes += 4 * total;
+        int64_t run = base;
+        const int32_t* rec = o.out_rec + pl->pair_base * 8;
+        int64_t* off = o.out_off + pl->pair_base;
+        for (int64_t k = 0; k < pl->n_pairs; ++k) { off[k] = run; run += (rec[8 * k + GOTOH_B200_REC_N_OPS] + 15) >> 4; }
+    }
+    return GOTOH_B200_OK;
+}
+
 int check_common(const void* ref_bytes, const int64_t* ref_off, int64_t n_refs, const int32_t* ref_idx,
                  const void* qry_bytes, const int64_t* qry_off, int64_t n_pairs, int32_t matrix_id,
-                 const int64_t* out_off) {
-    if (!ref_bytes || !ref_off || !qry_bytes || !qry_off || !out_off) return fail(GOTOH_B200_EINVAL, "NULL pointer argument");
+                 const int64_t* out_off, bool need_out_off = true) {
+    if (!ref_bytes || !ref_off || !qry_bytes || !qry_off || (need_out_off && !out_off)) return fail(GOTOH_B200_EINVAL, "NULL pointer argument");
     if (n_pairs < 0 || n_refs < 0) return fail(GOTOH_B200_EINVAL, "negative count");
     if (n_pairs > 0x7fffffffLL) return fail(GOTOH_B200_ERANGE, "more than 2^31-1 pairs in one call");
     if (!ref_idx && n_refs != n_pairs) return fail(GOTOH_B200_EINVAL, "ref_idx is NULL but n_refs != n_pairs");
@@ -1079,8 +1199,7 @@ DeviceCtx* ctx_for(int dev) {
 // slab s-1 overlap the kernels of slab s.
 int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
                      const int32_t* ref_idx, const uint8_t* qry_bytes, const int64_t* qry_off,
-                     int64_t lo, int64_t hi, int32_t gip, int32_t gep, int32_t term, int32_t matrix_id,
-                     uint8_t* out_ref, uint8_t* out_qry, const int64_t* out_off, int32_t* out_len, int32_t* out_score) {
+                     int64_t lo, int64_t hi, int32_t gip, int32_t gep, int32_t term, int32_t matrix_id, const OutSpec& out) {
     const double t_entry = now_ms();
     DeviceCtx* ctx = ctx_for(dev);
     if (!ctx) return fail(GOTOH_B200_ENOMEM, "out of host memory");
@@ -1111,6 +1230,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     for (int w = 0; w < nws; ++w) {
         plans[w].ws = &ctx->ws[w];
         plans[w].gip = gip; plans[w].gep = gep; plans[w].term = term ? 1 : 0; plans[w].matrix = matrix_id;
+        plans[w].out_mode = out.mode;
         plans[w].arena_budget_bytes = slab_budget;
         plans[w].task_limit = getenv("GOTOH_B200_TASK_LIMIT") ? atoi(getenv("GOTOH_B200_TASK_LIMIT")) : 0;   // measured: no gain over persistent warps
     }
@@ -1138,28 +1258,49 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     // not the pipeline's bottleneck: per slab the host needs about as long as the kernels (measured on B200).
     int builders = getenv("GOTOH_B200_BUILDERS") ? atoi(getenv("GOTOH_B200_BUILDERS")) : 2;
     builders = std::max(1, std::min(std::min(builders, (int)NBUILD), std::min(nslabs, nws)));
-    std::vector<int> rcs((size_t)builders, 0);
-    std::vector<std::string> msgs((size_t)builders);
-    std::atomic<int> failed(0);
+    std::vector<int> rcs((size_t)builders + 1, 0);        // last entry: the collector
+    std::vector<std::string> msgs((size_t)builders + 1);
     // Kernels are ENQUEUED in slab order (the builders pack in parallel, then take turns), and the forward kernel of slab
     // s waits for the forward kernel of slab s - depth: without this all slabs in flight time-slice the SMs, finish
     // together and then queue up on the copy engine while the builders - waiting for a drained workspace - leave the
     // GPU idle (B200 trace: 30 ms of a 173 ms call).  depth = 2 keeps one more forward kernel resident to fill the tail
     // of the one ahead; walk/emit/D2H of a slab overlap the forward kernels of the next ones.
     int depth = getenv("GOTOH_B200_FWD_DEPTH") ? atoi(getenv("GOTOH_B200_FWD_DEPTH")) : 2;
+    // Shared state of the builders and the collector.  EVERY change of `failed`, `next_enqueue` or `state` happens under
+    // order_mu and is followed by notify_all, so no waiter can miss it (a builder that failed outside the ordered section
+    // used to leave the other one asleep in order_cv.wait).
     std::mutex order_mu;
     std::condition_variable order_cv;
+    bool failed = false;
     int next_enqueue = 0;
     std::vector<int> slab_ws((size_t)nslabs, -1);
+    // tight / compact forms: 0 = not enqueued, 1 = kernels + phase A enqueued, 2 = phase B enqueued (workspace may be recycled once its stream drains)
+    const bool two_phase = out.mode != OUT_STRIDED;
+    std::vector<int> state((size_t)nslabs, 0);
+    auto fail_and_wake = [&](int who, int rc) {
+        std::lock_guard<std::mutex> g(order_mu);
+        if (!rcs[(size_t)who]) { rcs[(size_t)who] = rc; msgs[(size_t)who] = g_err; }
+        failed = true;
+        order_cv.notify_all();
+    };
+    auto is_failed = [&]() { std::lock_guard<std::mutex> g(order_mu); return failed; };
+    const bool inject_fetch_failure = getenv("GOTOH_B200_TEST_FAIL_FETCH") != nullptr;    // tests: a D2H enqueue that fails
     auto builder = [&](int b) {
-        if (cudaSetDevice(dev) != cudaSuccess) { rcs[(size_t)b] = GOTOH_B200_ECUDA; msgs[(size_t)b] = "cudaSetDevice failed"; failed = 1; order_cv.notify_all(); return; }
+        if (cudaSetDevice(dev) != cudaSuccess) { fail_and_wake(b, fail(GOTOH_B200_ECUDA, "cudaSetDevice failed")); return; }
         int mine = 0;
-        for (int slab = b; slab < nslabs && !failed.load(); slab += builders, ++mine) {
+        for (int slab = b; slab < nslabs && !is_failed(); slab += builders, ++mine) {
             // builder b owns workspaces b, b+builders, ...; its previous slab on that workspace must have drained
             const int per = nws / builders;
             gotoh_b200_plan* pl = &plans[b + builders * (mine % per)];
             int rc = GOTOH_B200_OK;
             const double t_a = now_ms();
+            if (two_phase && mine >= per) {
+                // the collector must have enqueued the result copy of the slab that used this workspace before
+                const int prev = slab - builders * per;
+                std::unique_lock<std::mutex> g(order_mu);
+                order_cv.wait(g, [&] { return state[(size_t)prev] == 2 || failed; });
+                if (failed) return;
+            }
             if (cudaStreamSynchronize(pl->ws->stream) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed");
             if (trace_on() && pl->ws->trace_slab >= 0) {
                 float k0 = 0, k1 = 0, d1 = 0;
@@ -1173,16 +1314,16 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
             for (double& x : g_trace_phase) x = 0;
             if (!rc) {
                 try {
-                    rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, cuts[(size_t)slab], cuts[(size_t)slab + 1], out_off);
+                    rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, cuts[(size_t)slab], cuts[(size_t)slab + 1], out.out_off_in);
                 } catch (const std::bad_alloc&) {
                     rc = fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
                 }
             }
             const double t_c = now_ms();
             {
-                std::unique_lock<std::mutex> lk(order_mu);
-                order_cv.wait(lk, [&] { return next_enqueue == slab || failed.load(); });
-                if (!rc && !failed.load()) {
+                std::unique_lock<std::mutex> g(order_mu);
+                order_cv.wait(g, [&] { return next_enqueue == slab || failed; });
+                if (!rc && !failed) {
                     slab_ws[(size_t)slab] = (int)(pl->ws - &ctx->ws[0]);
                     if (depth > 0 && slab - depth >= 0 && slab_ws[(size_t)(slab - depth)] >= 0 &&
                         cudaStreamWaitEvent(pl->ws->stream, ctx->ws[slab_ws[(size_t)(slab - depth)]].ev_fwd, 0) != cudaSuccess)
@@ -1192,28 +1333,66 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
                     if (!rc) rc = plan_run(pl, false, nullptr, nullptr);
                 }
                 next_enqueue = slab + 1;
-                if (rc) failed = 1;
+                if (rc && !rcs[(size_t)b]) { rcs[(size_t)b] = rc; msgs[(size_t)b] = g_err; failed = true; }
                 order_cv.notify_all();
+                if (failed) return;
             }
-            if (trace_on() && !rc) cudaEventRecord(pl->ws->ev[1], pl->ws->stream);
-            if (!rc) rc = plan_fetch(pl, out_ref, out_qry, out_len, out_score);
+            if (trace_on()) cudaEventRecord(pl->ws->ev[1], pl->ws->stream);
+            if (inject_fetch_failure && slab == 1) rc = fail(GOTOH_B200_ECUDA, "injected result-copy failure (GOTOH_B200_TEST_FAIL_FETCH)");
+            if (!rc) rc = two_phase ? plan_fetch_a(pl, out) : plan_fetch(pl, out.out_ref, out.out_qry, out.out_len, out.out_score);
             if (trace_on() && !rc) { cudaEventRecord(pl->ws->ev[2], pl->ws->stream); pl->ws->trace_slab = slab; }
             if (trace_on())
                 fprintf(stderr, "[gotoh_b200] dev %d builder %d slab %d pairs %lld: wait %.1f ms, build %.1f ms (refs %.1f pass1 %.1f pass2 %.1f cls %.1f path %.1f sort %.1f tasks %.1f alloc+h2d %.1f), enqueue %.1f ms\n",
                         dev, b, slab, (long long)(cuts[(size_t)slab + 1] - cuts[(size_t)slab]), t_b - t_a, t_c - t_b, g_trace_phase[0], g_trace_phase[1],
                         g_trace_phase[2], g_trace_phase[3], g_trace_phase[4], g_trace_phase[5], g_trace_phase[6], g_trace_phase[7], now_ms() - t_c);
-            if (rc) { rcs[(size_t)b] = rc; msgs[(size_t)b] = g_err; failed = 1; return; }
+            if (rc) { fail_and_wake(b, rc); return; }
+            if (two_phase) {
+                std::lock_guard<std::mutex> g(order_mu);
+                state[(size_t)slab] = 1;
+                order_cv.notify_all();
+            }
         }
     };
-    if (builders == 1) builder(0);
+    // The collector (tight / compact forms; the calling thread): in slab order, waits for a slab's phase A, learns its
+    // total, and enqueues the result copy to the next free position of the caller's buffer.
+    auto collector = [&]() {
+        int64_t base = out.cap_lo;
+        for (int slab = 0; slab < nslabs; ++slab) {
+            {
+                std::unique_lock<std::mutex> g(order_mu);
+                order_cv.wait(g, [&] { return state[(size_t)slab] >= 1 || failed; });
+                if (failed) return;
+            }
+            Workspace* ws = &ctx->ws[slab_ws[(size_t)slab]];
+            gotoh_b200_plan* pl = &plans[slab_ws[(size_t)slab]];
+            int rc = GOTOH_B200_OK;
+            if (cudaEventSynchronize(ws->ev_a) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "kernels of slab %d failed: %s", slab, cudaGetErrorString(cudaGetLastError()));
+            const int64_t total = rc ? 0 : *ws->h_total.p;
+            if (!rc && base + total > out.cap_hi)
+                rc = fail(GOTOH_B200_ECAPACITY, "result buffer too small: pairs %lld..%lld need %lld %s at offset %lld of a %lld-%s slice (the worst-case bound of gotoh_b200.h always suffices)",
+                          (long long)cuts[(size_t)slab], (long long)cuts[(size_t)slab + 1], (long long)total, out.mode == OUT_TIGHT ? "bytes" : "words",
+                          (long long)(base - out.cap_lo), (long long)(out.cap_hi - out.cap_lo), out.mode == OUT_TIGHT ? "byte" : "word");
+            if (!rc) rc = plan_fetch_b(pl, out, base, total);
+            if (rc) { fail_and_wake(builders, rc); return; }
+            base += total;
+            std::lock_guard<std::mutex> g(order_mu);
+            state[(size_t)slab] = 2;
+            order_cv.notify_all();
+        }
+    };
+    if (builders == 1 && !two_phase) builder(0);
     else {
         std::vector<std::thread> th;
         for (int b = 0; b < builders; ++b) th.emplace_back(builder, b);
+        if (two_phase) {
+            if (cudaSetDevice(dev) != cudaSuccess) fail_and_wake(builders, fail(GOTOH_B200_ECUDA, "cudaSetDevice failed"));
+            else collector();
+        }
         for (auto& t : th) t.join();
     }
     int rc = GOTOH_B200_OK;
     const double t_built = now_ms();
-    for (int b = 0; b < builders; ++b)
+    for (int b = 0; b <= builders; ++b)
         if (rcs[(size_t)b] && !rc) rc = fail(rcs[(size_t)b], "%s", msgs[(size_t)b].c_str());
     for (int w = 0; w < nws; ++w) {
         const cudaError_t e = cudaStreamSynchronize(ctx->ws[w].stream);
@@ -1304,17 +1483,12 @@ extern "C" void gotoh_b200_release_cache(void) {
         }
 }
 
-// One-shot form.  Shards contiguous pair ranges of (nearly) equal cell count across the
+// One-shot forms.  Shard contiguous pair ranges of (nearly) equal cell count across the
 // devices in device_mask; one host thread per device; no inter-device traffic.
-extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
-                                          const int32_t* ref_idx, const uint8_t* qry_bytes,
-                                          const int64_t* qry_off, int64_t n_pairs, int32_t gip, int32_t gep,
-                                          int32_t use_terminal, int32_t matrix_id, uint8_t* out_ref,
-                                          uint8_t* out_qry, const int64_t* out_off, int32_t* out_len,
-                                          int32_t* out_score, uint32_t device_mask) {
-    int rc = check_common(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, matrix_id, out_off);
-    if (rc) return rc;
-    if (!out_ref || !out_qry || !out_len || !out_score) return fail(GOTOH_B200_EINVAL, "NULL output pointer");
+namespace {
+int align_batch_impl(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs, const int32_t* ref_idx,
+                     const uint8_t* qry_bytes, const int64_t* qry_off, int64_t n_pairs, int32_t gip, int32_t gep,
+                     int32_t use_terminal, int32_t matrix_id, const OutSpec& out, int64_t cap, uint32_t device_mask) {
     const int ndev = gotoh_b200_device_count();
     if (ndev <= 0) return fail(GOTOH_B200_ENODEVICE, "no CUDA device is visible; libgotoh_b200 has no CPU path");
     if (n_pairs == 0) return GOTOH_B200_OK;
@@ -1329,12 +1503,18 @@ extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_
     const int D = (int)std::min<int64_t>((int64_t)devs.size(), n_pairs);
     std::vector<int64_t> cut(D + 1, 0);
     cut[D] = n_pairs;
+    std::vector<OutSpec> outs((size_t)D, out);
+    outs[0].cap_lo = 0; outs[(size_t)D - 1].cap_hi = cap;
     if (D > 1) {
-        std::vector<double> pre((size_t)n_pairs + 1, 0.0);
+        // tight / compact forms: each device fills its own slice of the caller's capacity, in proportion to the
+        // worst-case size of its pairs (bytes: M+N; words: ceil((M+N)/16))
+        std::vector<double> pre((size_t)n_pairs + 1, 0.0), wpre((size_t)n_pairs + 1, 0.0);
         for (int64_t k = 0; k < n_pairs; ++k) {
             const int64_t r = ref_idx ? ref_idx[k] : k;
             const double m = (r >= 0 && r < n_refs) ? (double)(ref_off[r + 1] - ref_off[r]) : 1.0;
-            pre[(size_t)k + 1] = pre[(size_t)k] + std::max(1.0, m) * std::max<double>(1.0, (double)(qry_off[k + 1] - qry_off[k]));
+            const double nq = (double)(qry_off[k + 1] - qry_off[k]);
+            pre[(size_t)k + 1] = pre[(size_t)k] + std::max(1.0, m) * std::max<double>(1.0, nq);
+            wpre[(size_t)k + 1] = wpre[(size_t)k] + (out.mode == OUT_COMPACT ? std::floor((m + nq + 15) / 16) : m + nq);
         }
         for (int d = 1; d < D; ++d) {
             const double target = pre[(size_t)n_pairs] * d / D;
@@ -1342,12 +1522,16 @@ extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_
             cut[d] = std::max(cut[d], cut[d - 1] + 1);
             cut[d] = std::min<int64_t>(cut[d], n_pairs - (D - d));
         }
+        for (int d = 1; d < D; ++d) {
+            const double f = wpre[(size_t)n_pairs] > 0 ? wpre[(size_t)cut[d]] / wpre[(size_t)n_pairs] : 0.0;
+            outs[(size_t)d].cap_lo = outs[(size_t)d - 1].cap_hi = (int64_t)std::floor((double)cap * f);
+        }
     }
     std::vector<int> rcs(D, 0);
     std::vector<std::string> msgs(D);
     auto work = [&](int d) {
         rcs[d] = run_device_range(devs[d], ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, cut[d], cut[d + 1],
-                                  gip, gep, use_terminal, matrix_id, out_ref, out_qry, out_off, out_len, out_score);
+                                  gip, gep, use_terminal, matrix_id, outs[(size_t)d]);
         if (rcs[d]) msgs[d] = g_err;
     };
     if (D == 1) work(0);
@@ -1358,6 +1542,79 @@ extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_
     }
     for (int d = 0; d < D; ++d)
         if (rcs[d]) return fail(rcs[d], "device %d: %s", devs[d], msgs[d].c_str());
+    return GOTOH_B200_OK;
+}
+}  // namespace
+
+extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
+                                          const int32_t* ref_idx, const uint8_t* qry_bytes,
+                                          const int64_t* qry_off, int64_t n_pairs, int32_t gip, int32_t gep,
+                                          int32_t use_terminal, int32_t matrix_id, uint8_t* out_ref,
+                                          uint8_t* out_qry, const int64_t* out_off, int32_t* out_len,
+                                          int32_t* out_score, uint32_t device_mask) {
+    int rc = check_common(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, matrix_id, out_off);
+    if (rc) return rc;
+    if (!out_ref || !out_qry || !out_len || !out_score) return fail(GOTOH_B200_EINVAL, "NULL output pointer");
+    OutSpec o;
+    o.mode = OUT_STRIDED; o.out_ref = out_ref; o.out_qry = out_qry; o.out_off_in = out_off; o.out_len = out_len; o.out_score = out_score;
+    return align_batch_impl(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, o, 0, device_mask);
+}
+
+extern "C" int32_t gotoh_b200_align_batch_tight(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
+                                                const int32_t* ref_idx, const uint8_t* qry_bytes,
+                                                const int64_t* qry_off, int64_t n_pairs, int32_t gip, int32_t gep,
+                                                int32_t use_terminal, int32_t matrix_id, uint8_t* out_ref,
+                                                uint8_t* out_qry, int64_t out_cap, int64_t* out_off, int32_t* out_len,
+                                                int32_t* out_score, uint32_t device_mask) {
+    int rc = check_common(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, matrix_id, nullptr, false);
+    if (rc) return rc;
+    if (!out_ref || !out_qry || !out_off || !out_len || !out_score || out_cap < 0) return fail(GOTOH_B200_EINVAL, "NULL output pointer or negative capacity");
+    OutSpec o;
+    o.mode = OUT_TIGHT; o.out_ref = out_ref; o.out_qry = out_qry; o.out_off = out_off; o.out_len = out_len; o.out_score = out_score;
+    return align_batch_impl(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, o, out_cap, device_mask);
+}
+
+extern "C" int32_t gotoh_b200_align_batch_compact(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
+                                                  const int32_t* ref_idx, const uint8_t* qry_bytes,
+                                                  const int64_t* qry_off, int64_t n_pairs, int32_t gip, int32_t gep,
+                                                  int32_t use_terminal, int32_t matrix_id, int32_t* out_rec,
+                                                  uint32_t* out_ops, int64_t out_ops_cap, int64_t* out_ops_off,
+                                                  uint32_t device_mask) {
+    int rc = check_common(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, matrix_id, nullptr, false);
+    if (rc) return rc;
+    if (!out_rec || !out_ops || !out_ops_off || out_ops_cap < 0) return fail(GOTOH_B200_EINVAL, "NULL output pointer or negative capacity");
+    OutSpec o;
+    o.mode = OUT_COMPACT; o.out_rec = out_rec; o.out_ops = out_ops; o.out_off = out_ops_off;
+    return align_batch_impl(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, o, out_ops_cap, device_mask);
+}
+
+// Host-ceiling probe: plain device-to-host copies into the caller's (pinned) buffer, CUDA-event timed.
+extern "C" int32_t gotoh_b200_d2h_probe(int32_t device, void* host_buf, int64_t bytes, int32_t reps, double* seconds) {
+    if (!host_buf || !seconds || bytes <= 0 || reps <= 0) return fail(GOTOH_B200_EINVAL, "d2h_probe: bad argument");
+    const int ndev = gotoh_b200_device_count();
+    if (ndev <= 0 || device < 0 || device >= ndev) return fail(GOTOH_B200_ENODEVICE, "device %d not present", device);
+    CU(cudaSetDevice(device));
+    // scratch of at most 1 GB, copied repeatedly to successive positions of the host buffer
+    const int64_t piece = std::min<int64_t>(bytes, (int64_t)1 << 30);
+    void* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)piece));
+    cudaStream_t st;
+    cudaEvent_t e0, e1;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaMemsetAsync(d, 0x2d, (size_t)piece, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventRecord(e0, st));
+    for (int r = 0; r < reps; ++r)
+        for (int64_t at = 0; at < bytes; at += piece)
+            CU(cudaMemcpyAsync((char*)host_buf + at, d, (size_t)std::min<int64_t>(piece, bytes - at), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(e1, st));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    *seconds = ms * 1e-3;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st); cudaFree(d);
     return GOTOH_B200_OK;
 }
 

@@ -993,6 +993,10 @@ struct WalkParams {
     int32_t* j0;
     int32_t* out_len;           // plan order
     int32_t gip, gep, term;
+    // tight / compact result forms: what the caller-order prefix sum (k_scan) runs over - the pair's aligned length in
+    // bytes (scan_words = 0) or its op-script length in 32-bit words (scan_words = 1); NULL for the strided form
+    int32_t* scan_in;
+    int32_t scan_words;
 };
 
 __global__ void __launch_bounds__(128) k_walk(const WalkParams p) {
@@ -1029,6 +1033,92 @@ __global__ void __launch_bounds__(128) k_walk(const WalkParams p) {
     p.i0[pi] = i;
     p.j0[pi] = j;
     p.out_len[pi] = k + n + right;
+    if (p.scan_in) p.scan_in[pr.orig] = p.scan_words ? ((n + 15) >> 4) : (k + n + right);
+}
+
+// ------------------------------------------------------------------------------------
+// Caller-order exclusive prefix sum of the per-pair result sizes (tight / compact result forms): out[k] = sum of
+// in[0..k), out[n] = total.  One CTA, tiles of 1024 x 8 elements, warp-shuffle scans; the input is at most a slab's
+// pairs (L2-resident), so one CTA is the simplest thing that is never on the critical path.
+// ------------------------------------------------------------------------------------
+enum { SCAN_THREADS = 1024, SCAN_ITEMS = 8 };
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int32_t* in, int64_t* out, int n) {
+    __shared__ long long warp_sum[32];
+    __shared__ long long carry_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_sh = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += SCAN_THREADS * SCAN_ITEMS) {
+        const int first = base + tid * SCAN_ITEMS;
+        long long v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+        for (int x = 0; x < SCAN_ITEMS; ++x) { v[x] = (first + x < n) ? (long long)in[first + x] : 0; sum += v[x]; }
+        long long inc = sum;                                   // inclusive scan of the thread sums within the warp
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += o; }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = warp_sum[lane], winc = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(0xffffffffu, winc, off); if (lane >= off) winc += o; }
+            warp_sum[lane] = winc - w;                         // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const long long carry = carry_sh;
+        long long run = carry + warp_sum[warp] + (inc - sum);
+#pragma unroll
+        for (int x = 0; x < SCAN_ITEMS; ++x) { if (first + x < n) out[first + x] = run; run += v[x]; }
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) carry_sh = run;           // last thread's running sum = total so far
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry_sh;
+}
+
+// ------------------------------------------------------------------------------------
+// Compact result form: per pair one 8-word record and its op script, packed at the caller-order offsets of k_scan.
+// One warp per pair.  (include/gotoh_b200.h: GOTOH_B200_REC_*)
+// ------------------------------------------------------------------------------------
+struct PackParams {
+    const PairInfo* pairs;
+    int32_t pair_count;
+    const uint32_t* ops;
+    const int32_t* nops;
+    const int32_t* i0;
+    const int32_t* j0;
+    const int32_t* end_i;
+    const int32_t* end_j;
+    const int32_t* out_len_plan;
+    const int32_t* score_plan;
+    const int64_t* off;            // caller order, words
+    int32_t* rec;                  // caller order, 8 words per pair
+    uint32_t* cops;
+};
+
+__global__ void __launch_bounds__(128) k_pack_ops(const PackParams p) {
+    const int lane = threadIdx.x & 31;
+    const int pi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pi >= p.pair_count) return;
+    const PairInfo pr = p.pairs[pi];
+    const int n = p.nops[pi];
+    const uint32_t* src = p.ops + pr.ops_off;
+    uint32_t* dst = p.cops + p.off[pr.orig];
+    for (int x = lane; x < ((n + 15) >> 4); x += 32) dst[x] = src[x];
+    if (lane < 8) {
+        int v;
+        switch (lane) {
+            case 0: v = p.score_plan[pi]; break;
+            case 1: v = p.out_len_plan[pi]; break;
+            case 2: v = p.i0[pi]; break;
+            case 3: v = p.j0[pi]; break;
+            case 4: v = p.end_i[pi]; break;
+            case 5: v = p.end_j[pi]; break;
+            case 6: v = n; break;
+            default: v = (pr.M < 65536 && pr.N < 65536) ? ((pr.M << 16) | pr.N) : -1; break;
+        }
+        p.rec[(int64_t)pr.orig * 8 + lane] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -1051,6 +1141,7 @@ struct EmitParams {
     uint8_t* out_qry;
     int32_t* out_len;              // caller order
     int32_t* out_score;            // caller order
+    const int64_t* tight_off;      // tight result form: caller-order byte offsets from k_scan (no stride tail); else NULL
 };
 
 __global__ void __launch_bounds__(128) k_emit(const EmitParams p) {
@@ -1061,8 +1152,9 @@ __global__ void __launch_bounds__(128) k_emit(const EmitParams p) {
     const PairInfo pr = p.pairs[pi];
     const uint8_t* a = p.ref_raw + pr.ref_pos;
     const uint8_t* b = p.qry + pr.qry_pos;
-    uint8_t* oa = p.out_ref + pr.out_off;
-    uint8_t* ob = p.out_qry + pr.out_off;
+    const int64_t ooff = p.tight_off ? p.tight_off[pr.orig] : pr.out_off;
+    uint8_t* oa = p.out_ref + ooff;
+    uint8_t* ob = p.out_qry + ooff;
     const int i0 = p.i0[pi], j0 = p.j0[pi], n = p.nops[pi];
     const int ei = p.end_i[pi], ej = p.end_j[pi];
     const uint32_t* ops = p.ops + pr.ops_off;
@@ -1095,7 +1187,7 @@ __global__ void __launch_bounds__(128) k_emit(const EmitParams p) {
     if (ei == pr.M && ej < pr.N) { for (int x = lane; x < pr.N - ej; x += 32) { oa[ro_base + x] = '-'; ob[ro_base + x] = b[ej + x]; } }
     else { for (int x = lane; x < pr.M - ei; x += 32) { oa[ro_base + x] = a[ei + x]; ob[ro_base + x] = '-'; } }
     // bytes between out_len and the caller's stride are defined as 0
-    for (int x = p.out_len_plan[pi] + lane; x < pr.out_cap; x += 32) { oa[x] = 0; ob[x] = 0; }
+    if (!p.tight_off) for (int x = p.out_len_plan[pi] + lane; x < pr.out_cap; x += 32) { oa[x] = 0; ob[x] = 0; }
 }
 
 }  // namespace gotoh

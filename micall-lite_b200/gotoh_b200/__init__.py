@@ -6,7 +6,7 @@ the batched form.  All of them run on the GPU through libgotoh_b200.so; importin
 never loads the CPU oracle and there is no CPU fallback.
 """
 from . import _ffi
-from ._ffi import AA_RB, HIV25, NT, GotohError, GotohInputError  # noqa: F401
+from ._ffi import AA_RB, HIV25, NT, GotohCapacityError, GotohError, GotohInputError  # noqa: F401
 from .api import Aligner, PinnedArray, Plan  # noqa: F401
 
 _aligner = None
@@ -34,8 +34,8 @@ def align_it_aa_rb(standard, seq, gap_init_penalty, gap_extend_penalty, /):
     return _get().align_it_aa_rb(standard, seq, gap_init_penalty, gap_extend_penalty)
 
 
-def align_batch(refs, queries, gip, gep, term=1, matrix=NT, ref_idx=None, devices=None):
-    return _get().align_batch(refs, queries, gip, gep, term, matrix, ref_idx, devices)
+def align_batch(refs, queries, gip, gep, term=1, matrix=NT, ref_idx=None, devices=None, compact=False):
+    return _get().align_batch(refs, queries, gip, gep, term, matrix, ref_idx, devices, compact)
 
 
 def device_count():

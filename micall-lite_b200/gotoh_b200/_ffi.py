@@ -11,7 +11,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(os.path.dirname(_PKG), "lib", "libgotoh_b200.so")
 
-OK, EINVAL, EEMPTY, EDOMAIN, ESENTINEL, ERANGE, ENODEVICE, ECUDA, ENOMEM, ETRACEBACK = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
+OK, EINVAL, EEMPTY, EDOMAIN, ESENTINEL, ERANGE, ENODEVICE, ECUDA, ENOMEM, ETRACEBACK, ECAPACITY = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10
 NT, HIV25, AA_RB = 0, 1, 2
 
 # every symbol include/gotoh_b200.h declares (tests check the library exports all of them)
@@ -21,6 +21,7 @@ SYMBOLS = (
     "gotoh_b200_plan_run", "gotoh_b200_plan_fetch", "gotoh_b200_plan_destroy",
     "gotoh_b200_plan_stat", "gotoh_b200_host_alloc", "gotoh_b200_host_free", "gotoh_b200_int_peak",
     "gotoh_b200_release_cache", "gotoh_b200_gotoh2_align_batch", "gotoh_b200_gotoh2_last_stats", "gotoh_b200_edit_distance_batch",
+    "gotoh_b200_align_batch_tight", "gotoh_b200_align_batch_compact", "gotoh_b200_d2h_probe",
 )
 
 
@@ -32,6 +33,10 @@ class GotohError(RuntimeError):
 
 class GotohInputError(GotohError, ValueError):
     """Input outside the reference's defined domain."""
+
+
+class GotohCapacityError(GotohError):
+    """Tight / compact result forms: the caller's result buffer was too small (retry with the worst-case bound)."""
 
 
 _vp, _i32, _i64, _u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32
@@ -53,6 +58,14 @@ class Library:
         lib.gotoh_b200_align_batch.restype = _i32
         lib.gotoh_b200_align_batch.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                                _vp, _vp, _vp, _vp, _vp, _u32]
+        lib.gotoh_b200_align_batch_tight.restype = _i32
+        lib.gotoh_b200_align_batch_tight.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
+                                                     _vp, _vp, _i64, _vp, _vp, _vp, _u32]
+        lib.gotoh_b200_align_batch_compact.restype = _i32
+        lib.gotoh_b200_align_batch_compact.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
+                                                       _vp, _vp, _i64, _vp, _u32]
+        lib.gotoh_b200_d2h_probe.restype = _i32
+        lib.gotoh_b200_d2h_probe.argtypes = [_i32, _vp, _i64, _i32, ctypes.POINTER(ctypes.c_double)]
         lib.gotoh_b200_plan_create.restype = _i32
         lib.gotoh_b200_plan_create.argtypes = [_i32, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                                _vp, ctypes.POINTER(_vp)]
@@ -87,6 +100,8 @@ class Library:
         msg = (self.lib.gotoh_b200_last_error() or b"").decode("utf-8", "replace")
         if rc in (EEMPTY, EDOMAIN, ESENTINEL, ERANGE):
             raise GotohInputError(rc, msg)
+        if rc == ECAPACITY:
+            raise GotohCapacityError(rc, msg)
         raise GotohError(rc, msg)
 
     def device_count(self):

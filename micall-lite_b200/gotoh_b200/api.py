@@ -21,7 +21,8 @@ import ctypes
 import numpy as np
 
 from . import _ffi, packing
-from ._ffi import AA_RB, HIV25, NT, GotohError, GotohInputError  # noqa: F401
+from ._ffi import AA_RB, HIV25, NT, GotohCapacityError, GotohError, GotohInputError  # noqa: F401
+from .compact import CompactAlignments
 
 
 class Aligner:
@@ -60,11 +61,78 @@ class Aligner:
         self._libobj.check(rc)
         return out_ref, out_qry, out_off, out_len, out_score
 
+    def _packed_args(self, ref_bytes, ref_off, ref_idx, qry_bytes, qry_off):
+        ref_bytes = np.ascontiguousarray(ref_bytes, dtype=np.uint8)
+        qry_bytes = np.ascontiguousarray(qry_bytes, dtype=np.uint8)
+        ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+        qry_off = np.ascontiguousarray(qry_off, dtype=np.int64)
+        ridx = None if ref_idx is None else np.ascontiguousarray(ref_idx, dtype=np.int32)
+        return ref_bytes, ref_off, ridx, qry_bytes, qry_off
+
+    def align_packed_tight(self, ref_bytes, ref_off, ref_idx, qry_bytes, qry_off, gip, gep, term, matrix,
+                           out=None, device_mask=1):
+        """Tight form (gotoh_b200_align_batch_tight): the library lays the aligned strings out back to back.
+        Returns (out_ref, out_qry, out_off[n], out_len, out_score); ``out`` = (out_ref, out_qry, out_off, out_len,
+        out_score) arrays to fill (e.g. pinned), out_ref/out_qry of equal capacity."""
+        ref_bytes, ref_off, ridx, qry_bytes, qry_off = self._packed_args(ref_bytes, ref_off, ref_idx, qry_bytes, qry_off)
+        n = len(qry_off) - 1
+        if out is None:
+            cap = int(packing.out_offsets(ref_off, ridx, qry_off)[-1])
+            out = (np.zeros(cap, np.uint8), np.zeros(cap, np.uint8), np.zeros(n, np.int64), np.zeros(n, np.int32),
+                   np.zeros(n, np.int32))
+        out_ref, out_qry, out_off, out_len, out_score = out
+        rc = self._lib.gotoh_b200_align_batch_tight(
+            ref_bytes.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1, None if ridx is None else ridx.ctypes.data,
+            qry_bytes.ctypes.data, qry_off.ctypes.data, n, int(gip), int(gep), int(bool(term)), int(matrix),
+            out_ref.ctypes.data, out_qry.ctypes.data, min(len(out_ref), len(out_qry)), out_off.ctypes.data,
+            out_len.ctypes.data, out_score.ctypes.data, int(device_mask))
+        self._libobj.check(rc)
+        return out_ref, out_qry, out_off, out_len, out_score
+
+    def align_packed_compact(self, ref_bytes, ref_off, ref_idx, qry_bytes, qry_off, gip, gep, term, matrix,
+                             out=None, device_mask=1):
+        """Compact form (gotoh_b200_align_batch_compact): per pair a record + op script, ~1/60 of the bytes of the
+        string forms.  Returns a ``CompactAlignments`` whose ``strings(k)`` / ``[k]`` render the reference's strings on
+        demand.  ``out`` = (rec[n*8] int32, ops uint32, ops_off[n] int64) arrays to fill; without it the op buffer is
+        sized for typical alignments and the call is repeated with the worst-case bound if it was too small."""
+        ref_bytes, ref_off, ridx, qry_bytes, qry_off = self._packed_args(ref_bytes, ref_off, ref_idx, qry_bytes, qry_off)
+        n = len(qry_off) - 1
+        args = (ref_bytes.ctypes.data, ref_off.ctypes.data, len(ref_off) - 1, None if ridx is None else ridx.ctypes.data,
+                qry_bytes.ctypes.data, qry_off.ctypes.data, n, int(gip), int(gep), int(bool(term)), int(matrix))
+        if out is not None:
+            rec, ops, ops_off = out
+            self._libobj.check(self._lib.gotoh_b200_align_batch_compact(
+                *args, rec.ctypes.data, ops.ctypes.data, len(ops), ops_off.ctypes.data, int(device_mask)))
+        else:
+            rlen = np.diff(ref_off)
+            rl = rlen if ridx is None else rlen[ridx]
+            ql = np.diff(qry_off)
+            worst = int(((rl + ql + 15) >> 4).sum())
+            typical = int(((np.minimum(rl, ql) * 5 // 4 + 47) >> 4).sum())      # path ~ the shorter sequence + gaps
+            rec = np.zeros(n * 8, np.int32)
+            ops_off = np.zeros(n, np.int64)
+            for cap in sorted({min(typical, worst), worst}):
+                ops = np.zeros(max(cap, 1), np.uint32)
+                rc = self._lib.gotoh_b200_align_batch_compact(*args, rec.ctypes.data, ops.ctypes.data, cap,
+                                                              ops_off.ctypes.data, int(device_mask))
+                if rc != _ffi.ECAPACITY or cap == worst:
+                    self._libobj.check(rc)
+                    break
+        return CompactAlignments(ref_bytes, ref_off, ridx, qry_bytes, qry_off, int(matrix), rec, ops, ops_off)
+
+    def d2h_probe(self, host_array, reps=1, device=0):
+        """Seconds for `reps` plain device-to-host copies filling host_array (gotoh_b200_d2h_probe)."""
+        v = ctypes.c_double(0.0)
+        self._libobj.check(self._lib.gotoh_b200_d2h_probe(int(device), host_array.ctypes.data, host_array.nbytes,
+                                                          int(reps), ctypes.byref(v)))
+        return v.value
+
     # ---- list-of-strings form ------------------------------------------------------------
-    def align_batch(self, refs, queries, gip, gep, term=1, matrix=NT, ref_idx=None, devices=None):
+    def align_batch(self, refs, queries, gip, gep, term=1, matrix=NT, ref_idx=None, devices=None, compact=False):
         """Align queries[k] against refs[ref_idx[k]] (or refs[k]; a single ref is shared by all).
 
-        Returns a list of (aligned_ref, aligned_query, score) in input order."""
+        Returns a list of (aligned_ref, aligned_query, score) in input order; with ``compact=True`` a
+        ``CompactAlignments`` (same items, rendered on demand from the op scripts - only ~100 B per pair leave the GPU)."""
         if isinstance(refs, (str, bytes)):
             refs = [refs]
         queries = list(queries)
@@ -82,7 +150,11 @@ class Aligner:
         if devices is not None:
             mask = 0
             for d in devices:
+                if not 0 <= int(d) < 32:
+                    raise ValueError("device index %r outside 0..31 (device_mask is 32 bits wide)" % (d,))
                 mask |= 1 << int(d)
+        if compact:
+            return self.align_packed_compact(rb, ro, ref_idx, qb, qo, gip, gep, term, matrix, device_mask=mask)
         o_ref, o_qry, o_off, o_len, o_score = self.align_packed(rb, ro, ref_idx, qb, qo, gip, gep, term, matrix,
                                                                 device_mask=mask)
         a = packing.unpack(o_ref, o_off, o_len)

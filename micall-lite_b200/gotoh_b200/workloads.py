@@ -55,42 +55,50 @@ def _windows(ref_arr, n, width, rng):
 
 
 def _substitute(rows, alphabet, rate, rng):
-    """Replace a fraction `rate` of characters by a different letter of `alphabet`."""
-    hit = rng.random(rows.shape) < rate
-    idx = np.searchsorted(np.sort(alphabet), rows)
-    order = np.argsort(alphabet)
-    rank = np.empty_like(order)
-    rank[order] = np.arange(len(alphabet))
-    # position of each char in `alphabet` (chars not in alphabet keep index 0: irrelevant, they get replaced)
-    sorted_alpha = alphabet[order]
-    pos = order[np.clip(idx, 0, len(alphabet) - 1)]
-    pos = np.where(sorted_alpha[np.clip(idx, 0, len(alphabet) - 1)] == rows, pos, 0)
-    shift = rng.integers(1, len(alphabet), size=rows.shape)
-    new = alphabet[(pos + shift) % len(alphabet)]
-    return np.where(hit, new, rows)
+    """Replace a fraction `rate` of characters by a different letter of `alphabet` (sparse: only the hit positions are
+    touched, so a 1 M x 251 batch costs O(hits), not O(cells))."""
+    rows = np.array(rows, dtype=np.uint8, order="C")     # private copy
+    flat = rows.reshape(-1)
+    k = int(rng.binomial(flat.size, rate))
+    pos = rng.integers(0, flat.size, size=k)
+    lut = np.zeros(256, dtype=np.int64)                       # letter -> index in `alphabet` (others: 0, they get replaced anyway)
+    lut[alphabet] = np.arange(len(alphabet))
+    shift = rng.integers(1, len(alphabet), size=k)
+    flat[pos] = alphabet[(lut[flat[pos]] + shift) % len(alphabet)]
+    return rows
 
 
 def _indels(rows, lens, alphabet, p_del, p_ins, max_len, rng, extra):
-    """At most one deletion and one insertion of 1..max_len characters per row."""
+    """At most one deletion and one insertion of 1..max_len characters per row (vectorised over the affected rows)."""
     n, w = rows.shape
-    out = np.zeros((n, w + extra), dtype=np.uint8)
+    W = w + extra
+    out = np.zeros((n, W), dtype=np.uint8)
     out[:, :w] = rows
     lens = lens.copy()
-    dele = np.nonzero(rng.random(n) < p_del)[0]
-    for k in dele:
-        d = int(rng.integers(1, max_len + 1))
-        if lens[k] - d < 8:
-            continue
-        p = int(rng.integers(0, lens[k] - d + 1))
-        out[k, p:lens[k] - d] = out[k, p + d:lens[k]]
-        lens[k] -= d
-    ins = np.nonzero(rng.random(n) < p_ins)[0]
-    for k in ins:
-        d = int(rng.integers(1, max_len + 1))
-        p = int(rng.integers(0, lens[k] + 1))
-        out[k, p + d:lens[k] + d] = out[k, p:lens[k]].copy()
-        out[k, p:p + d] = alphabet[rng.integers(0, len(alphabet), size=d)]
-        lens[k] += d
+    cols = np.arange(W)[None, :]
+    sel = np.nonzero(rng.random(n) < p_del)[0]
+    if len(sel):
+        d = rng.integers(1, max_len + 1, size=len(sel))
+        ok = lens[sel] - d >= 8
+        sel, d = sel[ok], d[ok]
+        p = (rng.random(len(sel)) * (lens[sel] - d + 1)).astype(np.int64)          # uniform in 0 .. len-d
+        src = np.minimum(cols + np.where(cols >= p[:, None], d[:, None], 0), W - 1)
+        sub = np.take_along_axis(out[sel], src, axis=1)
+        lens[sel] -= d
+        sub[cols >= lens[sel][:, None]] = 0
+        out[sel] = sub
+    sel = np.nonzero(rng.random(n) < p_ins)[0]
+    if len(sel):
+        d = rng.integers(1, max_len + 1, size=len(sel))
+        p = (rng.random(len(sel)) * (lens[sel] + 1)).astype(np.int64)              # uniform in 0 .. len
+        src = np.clip(cols - np.where(cols >= (p + d)[:, None], d[:, None], 0), 0, W - 1)
+        sub = np.take_along_axis(out[sel], src, axis=1)
+        fresh = alphabet[rng.integers(0, len(alphabet), size=sub.shape)]
+        new = (cols >= p[:, None]) & (cols < (p + d)[:, None])
+        sub[new] = fresh[new]
+        lens[sel] += d
+        sub[cols >= lens[sel][:, None]] = 0
+        out[sel] = sub
     return out, lens
 
 

@@ -114,6 +114,11 @@ def main():
         doc["x2_half_k6"] = count("k_forwardINS_5Vec16ELi6ELb0ELb1E", 4, 6, 2)
     except Exception as e:
         doc["x2_half_k6"] = {"error": str(e)}
+    # long pairs (C4): strip dataflow kernel, int32 cells, 8 lane-steps x 8 columns per block
+    try:
+        doc["x1_flow"] = count("k_forward_flowILi8E", 8, 8, 1)
+    except Exception as e:
+        doc["x1_flow"] = {"error": str(e)}
     # gotoh2 (live aligner) kernels: forward with tie bits, score-only forward, reverse sweep (4 lane-steps x 8 columns)
     for tag, pat, sh, per, npair in (("g2_forward", "k2fILi8ELb0ELb1", "SHFL.UP", 2, 1), ("g2_forward_score_only", "k2fILi8ELb0ELb0", "SHFL.UP", 2, 1),
                                      ("g2_forward_x2", "k2f_x2ILi8E", "SHFL.UP", 2, 2), ("g2_reverse", "k2rILi8ELb0", "SHFL.DOWN", 1, 1),
@@ -126,14 +131,14 @@ def main():
     if os.path.exists(prev):
         try:
             old = json.load(open(prev))
-            for key in ("ncu_dram_bytes_per_launch", "ncu_dram_bytes_per_cell", "ncu_note"):
+            for key in ("ncu_dram_bytes_per_launch", "ncu_dram_bytes_per_cell", "ncu_note", "ncu"):
                 if key in old:
                     doc[key] = old[key]
         except Exception:
             pass
     os.makedirs(os.path.dirname(prev), exist_ok=True)
     json.dump(doc, open(prev, "w"), indent=1)
-    for tag in ("x2", "x1", "x2_half_k6", "g2_forward", "g2_forward_score_only", "g2_forward_x2", "g2_reverse", "g2_reverse_k3", "g2_reverse_x2_k3"):
+    for tag in ("x2", "x1", "x2_half_k6", "x1_flow", "g2_forward", "g2_forward_score_only", "g2_forward_x2", "g2_reverse", "g2_reverse_k3", "g2_reverse_x2_k3"):
         d = doc[tag]
         if "error" in d:
             print(tag, d["error"])
