@@ -129,7 +129,7 @@ int32_t gotoh_b200_align_batch_tight(const uint8_t* ref_bytes, const int64_t* re
  * the inputs and this record (gotoh_b200/compact.py expands them on demand; tests compare with the string entry point
  * and the oracle byte for byte).  out_ops_cap = capacity of out_ops in 32-bit words; sum of ceil((M+N)/16) always
  * suffices, real alignments need ~ceil(min(M,N)/16)+1 per pair (GOTOH_B200_ECAPACITY names the need).  out_ops_off has
- * n_pairs entries (OUTPUT).  ~100 B per 251-nt read cross PCIe instead of 6.6 KB.
+ * n_pairs entries (OUTPUT); the scripts of different pairs follow each other in no particular order.  ~100 B per 251-nt read cross PCIe instead of 6.6 KB.
  */
 enum { GOTOH_B200_REC_SCORE = 0, GOTOH_B200_REC_OUT_LEN = 1, GOTOH_B200_REC_I0 = 2, GOTOH_B200_REC_J0 = 3,
        GOTOH_B200_REC_END_I = 4, GOTOH_B200_REC_END_J = 5, GOTOH_B200_REC_N_OPS = 6, GOTOH_B200_REC_M_N = 7,

@@ -820,7 +820,7 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
         CU(ws->d_out_qry.ensure((size_t)pl->out_bytes));
     }
     if (pl->out_mode != OUT_STRIDED) {
-        CU(ws->d_scan_in.ensure((size_t)n));
+        if (pl->out_mode == OUT_TIGHT) CU(ws->d_scan_in.ensure((size_t)n));
         CU(ws->d_scan_out.ensure((size_t)n + 1));
     }
     if (pl->out_mode == OUT_COMPACT) {
@@ -1045,8 +1045,8 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
         wp.end_i = ws->d_end_i.p; wp.end_j = ws->d_end_j.p; wp.score = ws->d_score.p;
         wp.ops = ws->d_ops.p; wp.nops = ws->d_nops.p; wp.i0 = ws->d_i0.p; wp.j0 = ws->d_j0.p;
         wp.out_len = ws->d_len_plan.p; wp.gip = pl->gip; wp.gep = pl->gep; wp.term = pl->term;
-        wp.scan_in = pl->out_mode != OUT_STRIDED ? ws->d_scan_in.p : nullptr;
-        wp.scan_words = pl->out_mode == OUT_COMPACT ? 1 : 0;
+        wp.scan_in = pl->out_mode == OUT_TIGHT ? ws->d_scan_in.p : nullptr;
+        wp.scan_words = 0;
         GOTOH_LAUNCH(k_walk, dim3((c.pair_count + 127) / 128), dim3(128), 0, ws->stream, wp);
         CU(cudaGetLastError());
         // strided form: this chunk's strings at the caller's offsets.  The tight / compact forms need every pair's
@@ -1064,19 +1064,23 @@ int plan_run(gotoh_b200_plan* pl, bool timed, float* device_ms, float* forward_m
     }
     if (pl->out_mode != OUT_STRIDED && pl->n_pairs > 0) {
         const int n = (int)pl->n_pairs;
-        GOTOH_LAUNCH(k_scan, dim3(1), dim3(SCAN_THREADS), 0, ws->stream, ws->d_scan_in.p, ws->d_scan_out.p, n);
-        CU(cudaGetLastError());
         if (pl->out_mode == OUT_TIGHT) {
+            GOTOH_LAUNCH(k_scan, dim3(1), dim3(SCAN_THREADS), 0, ws->stream, ws->d_scan_in.p, ws->d_scan_out.p, n, ws->h_total.p);
+            CU(cudaGetLastError());
             const int rc = launch_emit(pl, 0, n, ws->d_scan_out.p);
             if (rc) return rc;
         } else {
+            CU(cudaMemsetAsync(ws->d_scan_out.p + n, 0, sizeof(int64_t), ws->stream));
             PackParams pp;
             memset(&pp, 0, sizeof(pp));
             pp.pairs = ws->d_pairs.p; pp.pair_count = n; pp.ops = ws->d_ops.p; pp.nops = ws->d_nops.p;
             pp.i0 = ws->d_i0.p; pp.j0 = ws->d_j0.p; pp.end_i = ws->d_end_i.p; pp.end_j = ws->d_end_j.p;
             pp.out_len_plan = ws->d_len_plan.p; pp.score_plan = ws->d_score.p;
-            pp.off = ws->d_scan_out.p; pp.rec = ws->d_rec.p; pp.cops = ws->d_cops.p;
+            pp.off = ws->d_scan_out.p; pp.counter = reinterpret_cast<unsigned long long*>(ws->d_scan_out.p + n);
+            pp.rec = ws->d_rec.p; pp.cops = ws->d_cops.p;
             GOTOH_LAUNCH(k_pack_ops, dim3((n + 3) / 4), dim3(128), 0, ws->stream, pp);
+            CU(cudaGetLastError());
+            GOTOH_LAUNCH(k_publish, dim3(1), dim3(1), 0, ws->stream, pp.counter, ws->h_total.p);
             CU(cudaGetLastError());
         }
     }
@@ -1119,47 +1123,32 @@ struct OutSpec {
     int64_t cap_lo = 0, cap_hi = 0;      // tight / compact: this device's slice of the caller's capacity (bytes / words)
 };
 
-// Tight / compact forms, phase A: the per-pair arrays and the slab's total size; the event tells the host when it may
-// read the total and enqueue phase B (the result bytes themselves, whose count and position it only knows then).
-int plan_fetch_a(gotoh_b200_plan* pl, const OutSpec& o) {
+// Tight / compact forms.  Phase A (enqueued with the kernels) is only an event: the last kernel of plan_run has written
+// the slab's total size into mapped pinned memory (k_scan / k_publish), no copy-engine work is queued yet.
+int plan_fetch_a(gotoh_b200_plan* pl) {
+    CU(cudaEventRecord(pl->ws->ev_a, pl->ws->stream));
+    return GOTOH_B200_OK;
+}
+
+// Phase B (issued by the collector, in slab order, once the slab's kernels are done and its total is known): every
+// result copy of the slab - per-pair arrays, slab-local offsets (the caller adds `base` after the copies have landed,
+// see run_device_range) and the tightly packed result bytes at position `base` of the caller's buffer.
+int plan_fetch_b(gotoh_b200_plan* pl, const OutSpec& o, int64_t base, int64_t total) {
     Workspace* ws = pl->ws;
     pl->d2h_bytes = 0;
     auto d2h = [&](void* h, const void* d, size_t bytes) -> cudaError_t {
         pl->d2h_bytes += (int64_t)bytes;
-        return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ws->stream);
+        return bytes ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ws->stream) : cudaSuccess;
     };
+    CU(d2h(o.out_off + pl->pair_base, ws->d_scan_out.p, (size_t)pl->n_pairs * sizeof(int64_t)));
     if (o.mode == OUT_TIGHT) {
         CU(d2h(o.out_len + pl->pair_base, ws->d_out_len.p, (size_t)pl->n_pairs * sizeof(int32_t)));
         CU(d2h(o.out_score + pl->pair_base, ws->d_out_score.p, (size_t)pl->n_pairs * sizeof(int32_t)));
+        CU(d2h(o.out_ref + base, ws->d_out_ref.p, (size_t)total));
+        CU(d2h(o.out_qry + base, ws->d_out_qry.p, (size_t)total));
     } else {
         CU(d2h(o.out_rec + pl->pair_base * 8, ws->d_rec.p, (size_t)pl->n_pairs * 8 * sizeof(int32_t)));
-    }
-    CU(d2h(ws->h_total.p, ws->d_scan_out.p + pl->n_pairs, sizeof(int64_t)));
-    CU(cudaEventRecord(ws->ev_a, ws->stream));
-    return GOTOH_B200_OK;
-}
-
-// Phase B: the slab's result bytes, tightly packed, to position `base` of the caller's buffer; per-pair offsets are
-// the running sum of the sizes phase A brought back.
-int plan_fetch_b(gotoh_b200_plan* pl, const OutSpec& o, int64_t base, int64_t total) {
-    Workspace* ws = pl->ws;
-    if (o.mode == OUT_TIGHT) {
-        if (total > 0) {
-            CU(cudaMemcpyAsync(o.out_ref + base, ws->d_out_ref.p, (size_t)total, cudaMemcpyDeviceToHost, ws->stream));
-            CU(cudaMemcpyAsync(o.out_qry + base, ws->d_out_qry.p, (size_t)total, cudaMemcpyDeviceToHost, ws->stream));
-        }
-        pl->d2h_bytes += 2 * total;
-        int64_t run = base;
-        const int32_t* len = o.out_len + pl->pair_base;
-        int64_t* off = o.out_off + pl->pair_base;
-        for (int64_t k = 0; k < pl->n_pairs; ++k) { off[k] = run; run += len[k]; }
-    } else {
-        if (total > 0) CU(cudaMemcpyAsync(o.out_ops + base, ws->d_cops.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, ws->stream));
-        pl->d2h_bytes += 4 * total;
-        int64_t run = base;
-        const int32_t* rec = o.out_rec + pl->pair_base * 8;
-        int64_t* off = o.out_off + pl->pair_base;
-        for (int64_t k = 0; k < pl->n_pairs; ++k) { off[k] = run; run += (rec[8 * k + GOTOH_B200_REC_N_OPS] + 15) >> 4; }
+        CU(d2h(o.out_ops + base, ws->d_cops.p, (size_t)total * sizeof(uint32_t)));
     }
     return GOTOH_B200_OK;
 }
@@ -1301,7 +1290,11 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
                 order_cv.wait(g, [&] { return state[(size_t)prev] == 2 || failed; });
                 if (failed) return;
             }
+            const double t_a2 = now_ms();
             if (cudaStreamSynchronize(pl->ws->stream) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed");
+            if (trace_on() && two_phase)
+                fprintf(stderr, "[gotoh_b200] dev %d builder %d slab %d: workspace released by the collector at %.2f ms (waited %.2f), stream drained at %.2f ms\n",
+                        dev, b, slab, t_a2 - t_entry, t_a2 - t_a, now_ms() - t_entry);
             if (trace_on() && pl->ws->trace_slab >= 0) {
                 float k0 = 0, k1 = 0, d1 = 0;
                 cudaEventElapsedTime(&k0, ctx->ws[0].ev[3], pl->ws->ev[0]);
@@ -1339,7 +1332,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
             }
             if (trace_on()) cudaEventRecord(pl->ws->ev[1], pl->ws->stream);
             if (inject_fetch_failure && slab == 1) rc = fail(GOTOH_B200_ECUDA, "injected result-copy failure (GOTOH_B200_TEST_FAIL_FETCH)");
-            if (!rc) rc = two_phase ? plan_fetch_a(pl, out) : plan_fetch(pl, out.out_ref, out.out_qry, out.out_len, out.out_score);
+            if (!rc) rc = two_phase ? plan_fetch_a(pl) : plan_fetch(pl, out.out_ref, out.out_qry, out.out_len, out.out_score);
             if (trace_on() && !rc) { cudaEventRecord(pl->ws->ev[2], pl->ws->stream); pl->ws->trace_slab = slab; }
             if (trace_on())
                 fprintf(stderr, "[gotoh_b200] dev %d builder %d slab %d pairs %lld: wait %.1f ms, build %.1f ms (refs %.1f pass1 %.1f pass2 %.1f cls %.1f path %.1f sort %.1f tasks %.1f alloc+h2d %.1f), enqueue %.1f ms\n",
@@ -1355,6 +1348,8 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     };
     // The collector (tight / compact forms; the calling thread): in slab order, waits for a slab's phase A, learns its
     // total, and enqueues the result copy to the next free position of the caller's buffer.
+    struct SlabBase { int64_t pair_lo, n, base; };
+    std::vector<SlabBase> bases;                      // per slab: where its results went; offsets are slab-local until the end
     auto collector = [&]() {
         int64_t base = out.cap_lo;
         for (int slab = 0; slab < nslabs; ++slab) {
@@ -1366,14 +1361,20 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
             Workspace* ws = &ctx->ws[slab_ws[(size_t)slab]];
             gotoh_b200_plan* pl = &plans[slab_ws[(size_t)slab]];
             int rc = GOTOH_B200_OK;
+            const double t_seen = now_ms();
             if (cudaEventSynchronize(ws->ev_a) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "kernels of slab %d failed: %s", slab, cudaGetErrorString(cudaGetLastError()));
             const int64_t total = rc ? 0 : *ws->h_total.p;
             if (!rc && base + total > out.cap_hi)
                 rc = fail(GOTOH_B200_ECAPACITY, "result buffer too small: pairs %lld..%lld need %lld %s at offset %lld of a %lld-%s slice (the worst-case bound of gotoh_b200.h always suffices)",
                           (long long)cuts[(size_t)slab], (long long)cuts[(size_t)slab + 1], (long long)total, out.mode == OUT_TIGHT ? "bytes" : "words",
                           (long long)(base - out.cap_lo), (long long)(out.cap_hi - out.cap_lo), out.mode == OUT_TIGHT ? "byte" : "word");
+            const double t_ev = now_ms();
             if (!rc) rc = plan_fetch_b(pl, out, base, total);
             if (rc) { fail_and_wake(builders, rc); return; }
+            if (trace_on())
+                fprintf(stderr, "[gotoh_b200] dev %d collector slab %d: phase A seen at %.2f ms, done at %.2f ms, phase B enqueued at %.2f ms (total %lld)\n",
+                        dev, slab, t_seen - t_entry, t_ev - t_entry, now_ms() - t_entry, (long long)total);
+            bases.push_back({pl->pair_base, pl->n_pairs, base});
             base += total;
             std::lock_guard<std::mutex> g(order_mu);
             state[(size_t)slab] = 2;
@@ -1398,6 +1399,10 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
         const cudaError_t e = cudaStreamSynchronize(ctx->ws[w].stream);
         if (e != cudaSuccess && !rc) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
     }
+    // the copies have landed: turn the slab-local offsets into positions in the caller's buffer
+    if (!rc)
+        for (const SlabBase& sb : bases)
+            if (sb.base) { int64_t* off = out.out_off + sb.pair_lo; for (int64_t k = 0; k < sb.n; ++k) off[k] += sb.base; }
     if (trace_on())
         fprintf(stderr, "[gotoh_b200] dev %d call: setup+cuts %.2f ms (%d slabs), builders %.2f ms, drain %.2f ms\n", dev, t_cuts - t_entry, nslabs,
                 t_built - t_cuts, now_ms() - t_built);

@@ -1038,12 +1038,15 @@ __global__ void __launch_bounds__(128) k_walk(const WalkParams p) {
 
 // ------------------------------------------------------------------------------------
 // Caller-order exclusive prefix sum of the per-pair result sizes (tight / compact result forms): out[k] = sum of
-// in[0..k), out[n] = total.  One CTA, tiles of 1024 x 8 elements, warp-shuffle scans; the input is at most a slab's
-// pairs (L2-resident), so one CTA is the simplest thing that is never on the critical path.
+// in[0..k), out[n] = total.  One SMALL CTA (4 warps), tiles of 128 x 16 elements, warp-shuffle scans: in the one-shot
+// pipeline it has to find room on an SM next to the persistent forward CTAs of the following slabs (a 1024-thread CTA
+// needs most of an SM's registers and waited for a forward kernel to drain - measured on B200), and the input is at
+// most a slab's pairs (L2-resident).
 // ------------------------------------------------------------------------------------
-enum { SCAN_THREADS = 1024, SCAN_ITEMS = 8 };
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int32_t* in, int64_t* out, int n) {
-    __shared__ long long warp_sum[32];
+enum { SCAN_THREADS = 128, SCAN_ITEMS = 16 };
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int32_t* in, int64_t* out, int n, int64_t* total_host) {
+    enum { NW = SCAN_THREADS / 32 };
+    __shared__ long long warp_sum[NW];
     __shared__ long long carry_sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_sh = 0;
@@ -1058,11 +1061,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int32_t* in, int64_
         for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += o; }
         if (lane == 31) warp_sum[warp] = inc;
         __syncthreads();
-        if (warp == 0) {
-            long long w = warp_sum[lane], winc = w;
+        if (tid == 0) {                                        // exclusive prefix of the NW warp totals
+            long long run = 0;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { const long long o = __shfl_up_sync(0xffffffffu, winc, off); if (lane >= off) winc += o; }
-            warp_sum[lane] = winc - w;                         // exclusive prefix of the warp totals
+            for (int w = 0; w < NW; ++w) { const long long t = warp_sum[w]; warp_sum[w] = run; run += t; }
         }
         __syncthreads();
         const long long carry = carry_sh;
@@ -1073,12 +1075,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const int32_t* in, int64_
         if (tid == SCAN_THREADS - 1) carry_sh = run;           // last thread's running sum = total so far
         __syncthreads();
     }
-    if (tid == 0) out[n] = carry_sh;
+    if (tid == 0) { out[n] = carry_sh; *total_host = carry_sh; }     // total_host: mapped pinned memory, see k_publish
 }
 
+// The slab's total result size goes to the host through mapped pinned memory, written by a kernel: a D2H copy issued
+// at enqueue time would sit in the copy engine's FIFO in front of the result copies of EARLIER slabs (which the host
+// can only issue once it knows their totals) and block them until this slab's kernels are done - measured on B200.
+__global__ void k_publish(const unsigned long long* counter, int64_t* total_host) { *total_host = (int64_t)*counter; }
+
 // ------------------------------------------------------------------------------------
-// Compact result form: per pair one 8-word record and its op script, packed at the caller-order offsets of k_scan.
-// One warp per pair.  (include/gotoh_b200.h: GOTOH_B200_REC_*)
+// Compact result form: per pair one 8-word record and its op script.  The scripts are packed in the order the warps
+// get there (one atomicAdd on a word counter per pair; the per-pair offset is an explicit output of the call, so no
+// caller-order prefix sum - and no extra kernel between traceback and copy - is needed).  One warp per pair.
+// (include/gotoh_b200.h: GOTOH_B200_REC_*)
 // ------------------------------------------------------------------------------------
 struct PackParams {
     const PairInfo* pairs;
@@ -1091,7 +1100,8 @@ struct PackParams {
     const int32_t* end_j;
     const int32_t* out_len_plan;
     const int32_t* score_plan;
-    const int64_t* off;            // caller order, words
+    int64_t* off;                  // out, caller order: first word of the pair's script in cops
+    unsigned long long* counter;   // words handed out so far (zeroed per run; its final value is the slab's total)
     int32_t* rec;                  // caller order, 8 words per pair
     uint32_t* cops;
 };
@@ -1103,8 +1113,12 @@ __global__ void __launch_bounds__(128) k_pack_ops(const PackParams p) {
     const PairInfo pr = p.pairs[pi];
     const int n = p.nops[pi];
     const uint32_t* src = p.ops + pr.ops_off;
-    uint32_t* dst = p.cops + p.off[pr.orig];
-    for (int x = lane; x < ((n + 15) >> 4); x += 32) dst[x] = src[x];
+    const int nw = (n + 15) >> 4;
+    unsigned long long at = 0;
+    if (lane == 0) { at = atomicAdd(p.counter, (unsigned long long)nw); p.off[pr.orig] = (int64_t)at; }
+    at = __shfl_sync(0xffffffffu, at, 0);
+    uint32_t* dst = p.cops + at;
+    for (int x = lane; x < nw; x += 32) dst[x] = src[x];
     if (lane < 8) {
         int v;
         switch (lane) {

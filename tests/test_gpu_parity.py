@@ -209,19 +209,6 @@ def test_gpu_chunked_arena(gpu_aligner, oracle_port, monkeypatch):
     _check_packed(gpu_aligner, oracle_port, 0, rb, ro, np.zeros(400, np.int32), qb, qo, 10, 3, 1)
 
 
-def test_gpu_multi_device_sharding_matches_single(gpu_aligner):
-    """device_mask over every visible GPU gives the same bytes as device 0 alone."""
-    from gotoh_b200 import packing, workloads
-    nd = gpu_aligner.device_count()
-    ref, qb, qo = workloads.c2_reads_packed(3000, seed=10)
-    rb, ro = packing.pack([ref])
-    ridx = np.zeros(3000, np.int32)
-    one = gpu_aligner.align_packed(rb, ro, ridx, qb, qo, 10, 3, 1, 0, device_mask=1)
-    allm = gpu_aligner.align_packed(rb, ro, ridx, qb, qo, 10, 3, 1, 0, device_mask=(1 << nd) - 1)
-    assert (one[3] == allm[3]).all() and (one[4] == allm[4]).all()
-    assert (one[0] == allm[0]).all() and (one[1] == allm[1]).all()
-
-
 def test_gpu_int_peak_microbenchmarks_run(gpu_aligner):
     v = gpu_aligner.int_peak(2)
     assert v > 100.0   # G thread-instructions/s; a B200 does thousands

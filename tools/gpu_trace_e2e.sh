@@ -1,3 +1,8 @@
-# e2e of the one-shot call under different pipeline settings (diagnostics)
+# e2e of the one-shot calls, strings vs compact vs tight, with the library's per-slab trace (diagnostics)
 mkdir -p gpurun_out
-for mb in 2048 1536 1024 2560 2048; do GOTOH_B200_SLAB_MB=$mb python tools/trace_e2e.py --reps 5 2>/dev/null; done
+for cfg in "c4 1500" "c2 200000"; do set -- $cfg
+  for f in strings compact tight; do
+    python tools/trace_e2e.py --config $1 --pairs $2 --reps 3 --format $f 2>/dev/null
+    GOTOH_B200_TRACE=1 python tools/trace_e2e.py --config $1 --pairs $2 --reps 1 --format $f > /dev/null 2> gpurun_out/trace_$1_$f.log
+  done
+done
