@@ -177,7 +177,8 @@ void gotoh_b200_plan_destroy(gotoh_b200_plan* plan);
  *   0 total DP cells (sum M*N)          1 kernel launches per plan_run
  *   2 bytes copied H2D by plan_create   3 bytes copied D2H by plan_fetch
  *   4 direction-arena bytes in HBM      5 pairs on the 16-bit x2 path
- *   6 pairs on the 32-bit path          7 number of arena chunks per run */
+ *   6 pairs on the 32-bit path          7 number of arena chunks per run
+ *   8 1 if the plan was laid out by the device-side builder (csrc/gotoh_prep.cuh), 0 if by the host builder */
 int64_t gotoh_b200_plan_stat(const gotoh_b200_plan* plan, int32_t what);
 
 /* gotoh_b200_align_batch keeps three workspaces (device buffers, pinned staging, a stream) per

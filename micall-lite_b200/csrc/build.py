@@ -14,7 +14,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "lib", "libgotoh_b200.so")
 SOURCES = ["gotoh_b200.cu"]
-DEPS = ["gotoh_b200.cu", "gotoh_kernels.cuh", "gotoh_tables.h", "gotoh_intpeak.cuh", "gotoh2_kernels.cuh", "gotoh2_host.cuh", "gotoh2_fast.cuh"]
+DEPS = ["gotoh_b200.cu", "gotoh_kernels.cuh", "gotoh_tables.h", "gotoh_intpeak.cuh", "gotoh2_kernels.cuh", "gotoh2_host.cuh", "gotoh2_fast.cuh", "gotoh_prep.cuh", "gotoh_plan_math.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

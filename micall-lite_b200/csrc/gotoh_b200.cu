@@ -8,6 +8,7 @@
 #include "../../include/gotoh_b200.h"
 
 #include "gotoh_kernels.cuh"
+#include "gotoh_prep.cuh"
 #include "gotoh_tables.h"
 #include "gotoh_intpeak.cuh"
 
@@ -144,7 +145,14 @@ struct Workspace {
     DevBuf<int32_t> d_scan_in, d_rec;
     DevBuf<int64_t> d_scan_out;
     DevBuf<uint32_t> d_cops;
-    PinBuf<int64_t> h_total;        // the slab's total (bytes / words), copied back with the per-pair arrays (phase A)
+    // device-side plan builder (gotoh_prep.cuh): one carved scratch block, per-reference tables, summary in mapped pinned memory
+    DevBuf<uint8_t> d_prep;
+    PinBuf<uint8_t> h_prep;
+    PinBuf<PrepSummary> h_prep_sum;
+    cudaEvent_t ev_p = 0;
+    cudaEvent_t ev_done = 0;        // one-shot pipeline: recorded after a slab's last enqueued operation; the workspace is free once it fires
+    bool ev_done_pending = false;
+    PinBuf<int64_t> h_total;        // the slab's total (bytes / words), written by k_scan / k_publish into mapped pinned memory
     cudaEvent_t ev_a = 0;           // recorded after phase A: the host may read h_total and enqueue the result copy (phase B)
     // pinned staging
     PinBuf<uint8_t> h_ref_raw, h_ref_cls, h_qry;
@@ -162,8 +170,15 @@ struct Workspace {
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&ev[i]));
         CU(cudaEventCreateWithFlags(&ev_fwd, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
+        // events the host waits on.  Spin-waiting is the default: with cudaEventBlockingSync every wake-up cost ~0.2 ms on
+        // B200 hosts, which a pipeline of 1.2 ms slabs cannot afford (C2 one-shot call 153 -> 177 ms).  GOTOH_B200_BLOCKING_SYNC=1
+        // trades that latency for idle cores on hosts with fewer cores than waiting threads.
+        const unsigned evf = cudaEventDisableTiming | ((getenv("GOTOH_B200_BLOCKING_SYNC") && atoi(getenv("GOTOH_B200_BLOCKING_SYNC"))) ? cudaEventBlockingSync : 0);
+        CU(cudaEventCreateWithFlags(&ev_a, evf));
+        CU(cudaEventCreateWithFlags(&ev_p, evf));
+        CU(cudaEventCreateWithFlags(&ev_done, evf));
         CU(h_total.ensure(8));
+        CU(h_prep_sum.ensure(1));
         ready = true;
         return GOTOH_B200_OK;
     }
@@ -178,6 +193,9 @@ struct Workspace {
         d_counter.release();
         d_scan_in.release(); d_rec.release(); d_scan_out.release(); d_cops.release(); h_total.release();
         if (ev_a) { cudaEventDestroy(ev_a); ev_a = 0; }
+        if (ev_p) { cudaEventDestroy(ev_p); ev_p = 0; }
+        if (ev_done) { cudaEventDestroy(ev_done); ev_done = 0; }
+        d_prep.release(); h_prep.release(); h_prep_sum.release();
         h_ref_raw.release(); h_ref_cls.release(); h_qry.release(); h_pairs.release(); h_tasks.release(); h_table4.release();
         for (int i = 0; i < 4; ++i) if (ev[i]) { cudaEventDestroy(ev[i]); ev[i] = 0; }
         if (ev_fwd) { cudaEventDestroy(ev_fwd); ev_fwd = 0; }
@@ -209,6 +227,7 @@ enum { OUT_STRIDED = 0, OUT_TIGHT = 1, OUT_COMPACT = 2 };   // result forms (inc
 struct gotoh_b200_plan {
     Workspace* ws = nullptr;
     int out_mode = OUT_STRIDED;
+    bool built_on_device = false;          // the device plan builder (gotoh_prep.cuh) laid this plan out
     int64_t ops_words = 0;                 // op-script words of all pairs (capacity of d_ops / d_cops)
     bool owns_ws = false;
     int64_t n_pairs = 0;
@@ -237,7 +256,7 @@ struct gotoh_b200_plan {
 
 namespace {
 
-inline bool is_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+inline bool is_ws(uint8_t c) { return plan_is_ws(c); }
 
 // trim(): gotoh.cpp:545-559 (both ends, " \t\n\r").
 inline void trim_span(const uint8_t* s, int64_t n, int64_t* lo, int64_t* hi) {
@@ -247,43 +266,13 @@ inline void trim_span(const uint8_t* s, int64_t n, int64_t* lo, int64_t* hi) {
     *lo = a; *hi = b;
 }
 
-int pick_K(int n) {
-    for (int k : kSupportedK) if (32 * k >= n) return k;
-    return kMaxK;
-}
-// Queries of at most 128 columns run as two 16-lane wavefronts per warp (k_forward<..., HALF>): K columns per lane with
-// 16*K >= n.  GOTOH_B200_HALF=0 pins the 32-lane kernels (tests, A/B measurements; still a GPU path).
-thread_local bool t_half_off = false;    // read from the environment once per plan_build
-bool half_ok(int n) { return !t_half_off && n <= 16 * kMaxK; }
-int pick_K_half(int n) {
-    for (int k : kSupportedK) if (16 * k >= n) return k;
-    return kMaxK;
-}
-// kernel selector of an int16x2 pair: K, plus 16 when it runs on half-warp wavefronts
-int pick_KH(int n) { return half_ok(n) ? (16 | pick_K_half(n)) : pick_K(n); }
-
-// "range proof" for the int16x2 path: with rebase period R every value the Vec16 kernel
-// forms for real cells stays inside int16.  All quantities in stored units.
-// The stored frame is shifted up by z4 (a multiple of 4, one per plan) so that no stored S^ and no diagonal
-// candidate D^ is negative: the kernel then adds the packed substitution scores with one 32-bit multiply-add
-// (DESIGN.md 3.5b).  int16_low_need() is the smallest such shift for a pair.
-long long int16_low_need(int M, int N, int gip, int gep, int minT) {
-    const long long mn = std::min(M, N);
-    const long long smin = (long long)std::min(minT, 0) * mn;
-    const long long vmin = 4 * (smin - 2LL * gip - gep) - 8;
-    const long long add_lo = 4LL * std::max<long long>(gip, -(long long)std::min(minT, 0)) + 8;
-    return ((-(vmin - add_lo)) + 3) & ~3LL;
-}
+// per-pair decisions shared with the device builder: gotoh_plan_math.h
+thread_local bool t_half_off = false;    // GOTOH_B200_HALF=0 pins the 32-lane kernels (tests, A/B measurements); read once per plan_build
+int pick_K(int n) { return plan_pick_K(n); }
+int pick_KH(int n) { return plan_pick_KH(n, t_half_off); }
+long long int16_low_need(int M, int N, int gip, int gep, int minT) { return plan_int16_low_need(M, N, gip, gep, minT); }
 bool fits_int16(int M, int N, int K, int R, int gip, int gep, int minT, int maxT, long long z4) {
-    const long long mn = std::min(M, N);
-    const long long smax = (long long)std::max(maxT, 0) * mn;
-    const long long g = gep;
-    const long long vmax = 4 * (smax + (R + 32LL * K + 2) * g) + 8;
-    const long long add_hi = 4 * (std::max(maxT, 0) + 2 * g) + 4;
-    if (vmax + add_hi + z4 > 32000) return false;
-    if (int16_low_need(M, N, gip, gep, minT) > z4) return false;
-    if (4LL * R * g > 30000) return false;   // the rebase delta itself must be an int16
-    return true;
+    return plan_fits_int16(M, N, K, R, gip, gep, minT, maxT, z4);
 }
 
 struct HostPair {
@@ -434,6 +423,121 @@ int launch_forward_half(const gotoh_b200_plan* pl, const FwdParams& fp, int K, i
     return fail(GOTOH_B200_EINVAL, "unsupported K=%d", K);
 }
 
+// The references one plan uses: trimmed (+ degapped), validated, copied once into the pinned staging with REF_PAD zero
+// bytes on both sides, their byte classes and the compact score table.  O(reference bytes); shared by the host and the
+// device plan builders.
+struct RefSet {
+    std::vector<int32_t> ref_local;   // caller reference index -> local index (-1: unused); empty when ref_idx == NULL
+    std::vector<int64_t> used_refs;   // local index -> caller reference index
+    std::vector<int64_t> ref_pos;     // local index -> position of row 1 in h_ref_raw / h_ref_cls
+    std::vector<int32_t> ref_len;     // local index -> trimmed (degapped) length M
+    size_t ref_total = 0;
+    bool any_dollar3 = false;
+    std::vector<int> rep, rep_mask;   // class -> reference byte, stop-codon rule mask
+};
+
+int build_refs(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs, const int32_t* ref_idx,
+               int64_t pair_begin, int64_t pair_end, bool degap, RefSet& rs) {
+    Workspace* ws = pl->ws;
+    const int64_t n = pair_end - pair_begin;
+    const ScoreTable& tab = score_table(pl->matrix);
+    std::vector<int32_t>& ref_local = rs.ref_local;
+    std::vector<int64_t>& used_refs = rs.used_refs;
+    if (ref_idx) {
+        ref_local.assign((size_t)n_refs, -1);
+        for (int64_t k = pair_begin; k < pair_end; ++k) {
+            const int64_t r = ref_idx[k];
+            if (r < 0 || r >= n_refs) return fail(GOTOH_B200_EINVAL, "pair %lld: ref_idx %lld out of range", (long long)k, (long long)r);
+            if (ref_local[(size_t)r] < 0) { ref_local[(size_t)r] = (int32_t)used_refs.size(); used_refs.push_back(r); }
+        }
+    } else {
+        used_refs.resize((size_t)n);
+        for (int64_t k = 0; k < n; ++k) used_refs[(size_t)k] = pair_begin + k;
+    }
+    const size_t nu = used_refs.size();
+    std::vector<int64_t>& ref_pos = rs.ref_pos;
+    std::vector<int32_t>& ref_len = rs.ref_len;
+    std::vector<int64_t> ref_lo(nu);
+    ref_pos.resize(nu); ref_len.resize(nu);
+    size_t ref_total = REF_PAD;
+    for (size_t u = 0; u < nu; ++u) {
+        const int64_t r = used_refs[u];
+        if (ref_off[r + 1] < ref_off[r]) return fail(GOTOH_B200_EINVAL, "ref_off not monotone at %lld", (long long)r);
+        int64_t lo, hi;
+        trim_span(ref_bytes + ref_off[r], ref_off[r + 1] - ref_off[r], &lo, &hi);
+        ref_lo[u] = ref_off[r] + lo;
+        if (hi - lo >= (1 << 24)) return fail(GOTOH_B200_ERANGE, "reference %lld too long", (long long)r);
+        ref_len[u] = (int32_t)(hi - lo);             // upper bound; degap may shrink it below
+        ref_pos[u] = (int64_t)ref_total;
+        ref_total += (size_t)(hi - lo) + REF_PAD;
+    }
+    rs.ref_total = ref_total;
+    CU(ws->h_ref_raw.ensure(ref_total));
+    CU(ws->h_ref_cls.ensure(ref_total));
+    uint8_t* h_ref_raw = ws->h_ref_raw.p;
+    memset(h_ref_raw, 0, ref_total);
+    bool any_dollar3 = false;
+    for (size_t u = 0; u < nu; ++u) {
+        const uint8_t* s = ref_bytes + ref_lo[u];
+        uint8_t* dst = h_ref_raw + ref_pos[u];
+        const int len = ref_len[u];
+        int m = 0, dollars = 0;
+        for (int x = 0; x < len; ++x) {
+            const uint8_t c = s[x];
+            if (degap && c == '-') continue;                       // degap(): gotoh.cpp:529-543
+            if (c < 1 || c > 126) return fail(GOTOH_B200_EDOMAIN, "reference %lld: byte 0x%02x outside 1..126", (long long)used_refs[u], c);
+            dollars = (c == '$') ? dollars + 1 : 0;
+            if (dollars >= 3) any_dollar3 = true;                  // stop-codon bonus rule applies (gotoh.cpp:324-344)
+            dst[m++] = c;
+        }
+        if (m == 0) return fail(GOTOH_B200_EEMPTY, "reference %lld is empty after trim", (long long)used_refs[u]);
+        ref_len[u] = m;
+    }
+    rs.any_dollar3 = any_dollar3;
+    // classes of reference bytes, compact table.  A class is a distinct reference byte - or, in references that contain
+    // "$$$", a distinct (byte, rmask) where rmask says which of the three stop-codon bonus rules (gotoh.cpp:324-344)
+    // can fire in that row: bit0 a[i-3..i-1], bit1 a[i-2..i], bit2 a[i-1..i+1] == "$$$" (i >= 3).
+    // The +6 bonuses then live in the query profile and the kernel needs no extra work per cell.
+    uint8_t* h_ref_cls = ws->h_ref_cls.p;
+    memset(h_ref_cls, 0, ref_total);
+    int cls_of[128][8];
+    memset(cls_of, 0, sizeof(cls_of));
+    std::vector<int>& rep = rs.rep;
+    std::vector<int>& rep_mask = rs.rep_mask;
+    rep.assign(1, 0); rep_mask.assign(1, 0);
+    for (size_t u = 0; u < nu; ++u) {
+        const uint8_t* a = h_ref_raw + ref_pos[u];
+        const int M = ref_len[u];
+        for (int i = 1; i <= M; ++i) {
+            int rm = 0;
+            if (any_dollar3 && i >= 3) {
+                auto dol = [&](int p0) { return p0 >= 0 && p0 + 2 < M && a[p0] == '$' && a[p0 + 1] == '$' && a[p0 + 2] == '$'; };
+                rm = (dol(i - 3) ? 1 : 0) | (dol(i - 2) ? 2 : 0) | (dol(i - 1) ? 4 : 0);
+            }
+            const int c = a[i - 1];
+            if (!cls_of[c][rm]) {
+                if (rep.size() >= 250) return fail(GOTOH_B200_ERANGE, "more than 249 reference byte classes");
+                cls_of[c][rm] = (int)rep.size(); rep.push_back(c); rep_mask.push_back(rm);
+            }
+            h_ref_cls[ref_pos[u] + i - 1] = (uint8_t)cls_of[c][rm];
+        }
+    }
+    pl->ncls = (int)rep.size();
+    pl->has_dollar = any_dollar3 ? 1 : 0;
+    CU(ws->h_table4.ensure((size_t)pl->ncls * 136));
+    int32_t* h_table4 = ws->h_table4.p;           // [ncls][128] scores, then [ncls][8] bonuses
+    memset(h_table4, 0, (size_t)pl->ncls * 136 * sizeof(int32_t));
+    for (int c = 1; c < pl->ncls; ++c) {
+        for (int b = 1; b < 127; ++b) h_table4[(size_t)c * 128 + b] = 4 * (tab.v[rep[(size_t)c]][b] + 2 * pl->gep);
+        for (int cm = 0; cm < 8; ++cm) {
+            int bits = rep_mask[(size_t)c] & cm, cnt = 0;
+            while (bits) { cnt += bits & 1; bits >>= 1; }
+            h_table4[(size_t)pl->ncls * 128 + (size_t)c * 8 + cm] = 4 * 6 * cnt;
+        }
+    }
+    return GOTOH_B200_OK;
+}
+
 // Validate + trim (+ degap) + pack one contiguous range of caller pairs into the workspace's
 // pinned staging, choose the kernel path per pair, form warp tasks and arena chunks, and
 // enqueue the H2D copies on the workspace stream (no synchronisation).
@@ -452,58 +556,22 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
 
     double tph = now_ms();
     auto phase = [&](int k) { const double t = now_ms(); g_trace_phase[k] += t - tph; tph = t; };
-    // ---- references used by this range: trim, degap, validate, classes ------------------
-    std::vector<int32_t> ref_local;
-    std::vector<int64_t> used_refs;
-    if (ref_idx) {
-        ref_local.assign((size_t)n_refs, -1);
-        for (int64_t k = pair_begin; k < pair_end; ++k) {
-            const int64_t r = ref_idx[k];
-            if (r < 0 || r >= n_refs) return fail(GOTOH_B200_EINVAL, "pair %lld: ref_idx %lld out of range", (long long)k, (long long)r);
-            if (ref_local[(size_t)r] < 0) { ref_local[(size_t)r] = (int32_t)used_refs.size(); used_refs.push_back(r); }
-        }
-    } else {
-        used_refs.resize((size_t)n);
-        for (int64_t k = 0; k < n; ++k) used_refs[(size_t)k] = pair_begin + k;
+    // ---- references used by this range: trim, degap, validate, classes, score table ---------
+    RefSet rs;
+    {
+        const int rc = build_refs(pl, ref_bytes, ref_off, n_refs, ref_idx, pair_begin, pair_end, degap, rs);
+        if (rc) return rc;
     }
-    const size_t nu = used_refs.size();
-    std::vector<int64_t> ref_pos(nu), ref_lo(nu);
-    std::vector<int32_t> ref_len(nu);
-    size_t ref_total = REF_PAD;
-    for (size_t u = 0; u < nu; ++u) {
-        const int64_t r = used_refs[u];
-        if (ref_off[r + 1] < ref_off[r]) return fail(GOTOH_B200_EINVAL, "ref_off not monotone at %lld", (long long)r);
-        int64_t lo, hi;
-        trim_span(ref_bytes + ref_off[r], ref_off[r + 1] - ref_off[r], &lo, &hi);
-        ref_lo[u] = ref_off[r] + lo;
-        if (hi - lo >= (1 << 24)) return fail(GOTOH_B200_ERANGE, "reference %lld too long", (long long)r);
-        ref_len[u] = (int32_t)(hi - lo);             // upper bound; degap may shrink it below
-        ref_pos[u] = (int64_t)ref_total;
-        ref_total += (size_t)(hi - lo) + REF_PAD;
-    }
-    CU(ws->h_ref_raw.ensure(ref_total));
-    CU(ws->h_ref_cls.ensure(ref_total));
+    const std::vector<int32_t>& ref_local = rs.ref_local;
+    const std::vector<int64_t>& ref_pos = rs.ref_pos;
+    const std::vector<int32_t>& ref_len = rs.ref_len;
+    const size_t nu = rs.used_refs.size();
+    const size_t ref_total = rs.ref_total;
+    const bool any_dollar3 = rs.any_dollar3;
     uint8_t* h_ref_raw = ws->h_ref_raw.p;
-    memset(h_ref_raw, 0, ref_total);
-    bool ref_present[128] = {false}, qry_present[128] = {false};
-    bool any_dollar3 = false;
-    for (size_t u = 0; u < nu; ++u) {
-        const uint8_t* s = ref_bytes + ref_lo[u];
-        uint8_t* dst = h_ref_raw + ref_pos[u];
-        const int len = ref_len[u];
-        int m = 0, dollars = 0;
-        for (int x = 0; x < len; ++x) {
-            const uint8_t c = s[x];
-            if (degap && c == '-') continue;                       // degap(): gotoh.cpp:529-543
-            if (c < 1 || c > 126) return fail(GOTOH_B200_EDOMAIN, "reference %lld: byte 0x%02x outside 1..126", (long long)used_refs[u], c);
-            dollars = (c == '$') ? dollars + 1 : 0;
-            if (dollars >= 3) any_dollar3 = true;                  // stop-codon bonus rule applies (gotoh.cpp:324-344)
-            ref_present[c] = true;
-            dst[m++] = c;
-        }
-        if (m == 0) return fail(GOTOH_B200_EEMPTY, "reference %lld is empty after trim", (long long)used_refs[u]);
-        ref_len[u] = m;
-    }
+    uint8_t* h_ref_cls = ws->h_ref_cls.p;
+    int32_t* h_table4 = ws->h_table4.p;
+    bool qry_present[128] = {false};
 
     phase(0);
     // ---- queries, pass 1 (parallel): trim span, validate, length after degap, byte presence ----
@@ -604,51 +672,11 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     });
 
     phase(2);
-    // ---- classes of reference bytes, compact table, score range ----------------------------
-    // A class is a distinct reference byte - or, in references that contain "$$$", a distinct
-    // (byte, rmask) where rmask says which of the three stop-codon bonus rules (gotoh.cpp:324-344)
-    // can fire in that row: bit0 a[i-3..i-1], bit1 a[i-2..i], bit2 a[i-1..i+1] == "$$$" (i >= 3).
-    // The +6 bonuses then live in the query profile and the kernel needs no extra work per cell.
-    uint8_t* h_ref_cls = ws->h_ref_cls.p;
-    memset(h_ref_cls, 0, ref_total);
-    int cls_of[128][8];
-    memset(cls_of, 0, sizeof(cls_of));
-    std::vector<int> rep(1, 0), rep_mask(1, 0);
-    for (size_t u = 0; u < nu; ++u) {
-        const uint8_t* a = h_ref_raw + ref_pos[u];
-        const int M = ref_len[u];
-        for (int i = 1; i <= M; ++i) {
-            int rm = 0;
-            if (any_dollar3 && i >= 3) {
-                auto dol = [&](int p0) { return p0 >= 0 && p0 + 2 < M && a[p0] == '$' && a[p0 + 1] == '$' && a[p0 + 2] == '$'; };
-                rm = (dol(i - 3) ? 1 : 0) | (dol(i - 2) ? 2 : 0) | (dol(i - 1) ? 4 : 0);
-            }
-            const int c = a[i - 1];
-            if (!cls_of[c][rm]) {
-                if (rep.size() >= 250) return fail(GOTOH_B200_ERANGE, "more than 249 reference byte classes");
-                cls_of[c][rm] = (int)rep.size(); rep.push_back(c); rep_mask.push_back(rm);
-            }
-            h_ref_cls[ref_pos[u] + i - 1] = (uint8_t)cls_of[c][rm];
-        }
-    }
-    pl->ncls = (int)rep.size();
-    pl->has_dollar = any_dollar3 ? 1 : 0;
-    CU(ws->h_table4.ensure((size_t)pl->ncls * 136));
-    int32_t* h_table4 = ws->h_table4.p;           // [ncls][128] scores, then [ncls][8] bonuses
-    memset(h_table4, 0, (size_t)pl->ncls * 136 * sizeof(int32_t));
+    // ---- score range over the bytes present in the queries (the int16 proof depends on it) --------
     int minT = 0, maxT = 0;
-    for (int c = 1; c < pl->ncls; ++c) {
-        for (int b = 1; b < 127; ++b) {
-            const int t = tab.v[rep[c]][b];
-            h_table4[(size_t)c * 128 + b] = 4 * (t + 2 * pl->gep);
-            if (qry_present[b]) { minT = std::min(minT, t); maxT = std::max(maxT, t); }
-        }
-        for (int cm = 0; cm < 8; ++cm) {
-            int bits = rep_mask[c] & cm, cnt = 0;
-            while (bits) { cnt += bits & 1; bits >>= 1; }
-            h_table4[(size_t)pl->ncls * 128 + (size_t)c * 8 + cm] = 4 * 6 * cnt;
-        }
-    }
+    for (int c = 1; c < pl->ncls; ++c)
+        for (int b = 1; b < 127; ++b)
+            if (qry_present[b]) { const int t = tab.v[rs.rep[(size_t)c]][b]; minT = std::min(minT, t); maxT = std::max(maxT, t); }
     if (any_dollar3) maxT += 18;                   // up to three +6 bonuses on one cell
 
     phase(3);
@@ -960,6 +988,183 @@ int plan_build(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     return GOTOH_B200_OK;
 }
 
+// Device-side plan builder (gotoh_prep.cuh) for the common batch shape: many short queries against at most PREP_MAX_REFS
+// shared references, every pair admitted to the int16x2 kernels.  The host touches the references only; the queries go
+// to the device as they are and five small kernels trim, validate, admit, group and lay them out.  *done = false (and
+// nothing else changed that matters) means "not this path": the caller then runs the host builder, which also reports
+// every input error.  One event synchronisation per plan (the summary comes back through mapped pinned memory).
+int plan_build_device(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
+                      const int32_t* ref_idx, const uint8_t* qry_bytes, const int64_t* qry_off,
+                      int64_t pair_begin, int64_t pair_end, const int64_t* out_off, bool* done) {
+    *done = false;
+    pl->built_on_device = false;
+    Workspace* ws = pl->ws;
+    const int64_t n = pair_end - pair_begin;
+    const char* sw = getenv("GOTOH_B200_DEVICE_PREP");            // 0: host builder only; 1: also for small batches (tests)
+    const int mode = sw ? atoi(sw) : -1;
+    if (mode == 0) return GOTOH_B200_OK;
+    if (!ref_idx || pl->matrix == GOTOH_B200_AA_RB || n_refs > 4096 || n > 0x3fffffff) return GOTOH_B200_OK;
+    if (n < (mode == 1 ? 1 : 4096)) return GOTOH_B200_OK;        // small batches: the host builder costs less than a synchronisation
+    if (pl->gip < 0 || pl->gep < 0 || pl->gip > 100000 || pl->gep > 100000) return GOTOH_B200_OK;
+    if (getenv("GOTOH_B200_FORCE_PATH") && atoi(getenv("GOTOH_B200_FORCE_PATH")) == 32) return GOTOH_B200_OK;
+    const int64_t qbytes = qry_off[pair_end] - qry_off[pair_begin];
+    if (qbytes <= 0 || qbytes > ((int64_t)1 << 31)) return GOTOH_B200_OK;
+    CU(cudaSetDevice(ws->device));
+    double tph = now_ms();
+    auto phase = [&](int k) { const double t = now_ms(); g_trace_phase[k] += t - tph; tph = t; };
+    RefSet rs;
+    if (build_refs(pl, ref_bytes, ref_off, n_refs, ref_idx, pair_begin, pair_end, false, rs)) return GOTOH_B200_OK;
+    const int nu = (int)rs.used_refs.size();
+    if (nu > PREP_MAX_REFS) return GOTOH_B200_OK;
+    phase(0);
+    // references ranked in the order of the host builder's sort key: M descending, then index
+    std::vector<int> order((size_t)nu);
+    for (int u = 0; u < nu; ++u) order[(size_t)u] = u;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return rs.ref_len[(size_t)a] != rs.ref_len[(size_t)b] ? rs.ref_len[(size_t)a] > rs.ref_len[(size_t)b] : a < b; });
+    // ---- carve the scratch block ----------------------------------------------------------------------
+    const size_t nbins = (size_t)PREP_NKH * nu * PREP_NSLOT, ngrp = (size_t)PREP_NKH * nu;
+    size_t at = 0;
+    auto take = [&](size_t bytes) { const size_t o = (at + 15) & ~(size_t)15; at = o + bytes; return o; };
+    const size_t o_zero0 = take(0);
+    const size_t o_present = take(16), o_scal = take(32 * 4), o_acc = take(16), o_hist = take(nbins * 4), o_cursor = take(nbins * 4);
+    const size_t o_zero1 = take(0);
+    const size_t o_bin_pair = take((nbins + 1) * 8), o_bin_ops = take((nbins + 1) * 8), o_grp = take(ngrp * 3 * 8);
+    const size_t o_N = take((size_t)n * 4), o_lo = take((size_t)n * 4);
+    const size_t o_qoff = take((size_t)(n + 1) * 8), o_ridx = take((size_t)n * 4), o_ooff = take(out_off ? (size_t)(n + 1) * 8 : 0);
+    const size_t o_refM = take((size_t)n_refs * 4), o_refrank = take((size_t)n_refs * 4), o_refpos = take((size_t)n_refs * 8), o_rankM = take((size_t)nu * 4);
+    const size_t reftab_bytes = at - o_refM;
+    CU(ws->d_prep.ensure(at));
+    CU(ws->h_prep.ensure(reftab_bytes));
+    uint8_t* d = ws->d_prep.p;
+    {
+        int32_t* h_refM = reinterpret_cast<int32_t*>(ws->h_prep.p + (o_refM - o_refM));
+        int32_t* h_refrank = reinterpret_cast<int32_t*>(ws->h_prep.p + (o_refrank - o_refM));
+        int64_t* h_refpos = reinterpret_cast<int64_t*>(ws->h_prep.p + (o_refpos - o_refM));
+        int32_t* h_rankM = reinterpret_cast<int32_t*>(ws->h_prep.p + (o_rankM - o_refM));
+        memset(ws->h_prep.p, 0, reftab_bytes);
+        for (int64_t r = 0; r < n_refs; ++r) h_refrank[r] = -1;
+        for (int rank = 0; rank < nu; ++rank) {
+            const int u = order[(size_t)rank];
+            const int64_t r = rs.used_refs[(size_t)u];
+            h_refM[r] = rs.ref_len[(size_t)u]; h_refrank[r] = rank; h_refpos[r] = rs.ref_pos[(size_t)u];
+            h_rankM[rank] = rs.ref_len[(size_t)u];
+        }
+    }
+    // ---- H2D: references (as the host builder), the raw queries and the caller's offset arrays ------------------
+    CU(ws->d_ref_raw.ensure(rs.ref_total));
+    CU(ws->d_ref_cls.ensure(rs.ref_total));
+    CU(ws->d_table4.ensure((size_t)pl->ncls * 136));
+    CU(ws->d_qry.ensure((size_t)qbytes + 64));
+    pl->h2d_bytes = 0;
+    auto h2d = [&](void* dd, const void* h, size_t bytes) -> cudaError_t {
+        pl->h2d_bytes += (int64_t)bytes;
+        return cudaMemcpyAsync(dd, h, bytes, cudaMemcpyHostToDevice, ws->stream);
+    };
+    CU(h2d(ws->d_ref_raw.p, ws->h_ref_raw.p, rs.ref_total));
+    CU(h2d(ws->d_ref_cls.p, ws->h_ref_cls.p, rs.ref_total));
+    CU(h2d(ws->d_table4.p, ws->h_table4.p, (size_t)pl->ncls * 136 * sizeof(int32_t)));
+    CU(h2d(ws->d_qry.p, qry_bytes + qry_off[pair_begin], (size_t)qbytes));
+    CU(cudaMemsetAsync(ws->d_qry.p + qbytes, 0, 64, ws->stream));
+    CU(h2d(d + o_qoff, qry_off + pair_begin, (size_t)(n + 1) * 8));
+    CU(h2d(d + o_ridx, ref_idx + pair_begin, (size_t)n * 4));
+    if (out_off) CU(h2d(d + o_ooff, out_off + pair_begin, (size_t)(n + 1) * 8));
+    CU(h2d(d + o_refM, ws->h_prep.p, reftab_bytes));
+    CU(cudaMemsetAsync(d + o_zero0, 0, o_zero1 - o_zero0, ws->stream));
+    phase(1);
+    PrepParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.qry = ws->d_qry.p; pp.qry_off = reinterpret_cast<const int64_t*>(d + o_qoff); pp.ref_idx = reinterpret_cast<const int32_t*>(d + o_ridx);
+    pp.out_off = out_off ? reinterpret_cast<const int64_t*>(d + o_ooff) : nullptr;
+    pp.n = (int32_t)n; pp.n_refs = (int32_t)n_refs;
+    pp.ref_M = reinterpret_cast<const int32_t*>(d + o_refM); pp.ref_pos = reinterpret_cast<const int64_t*>(d + o_refpos);
+    pp.ref_rank = reinterpret_cast<const int32_t*>(d + o_refrank); pp.n_used = nu; pp.rank_M = reinterpret_cast<const int32_t*>(d + o_rankM);
+    pp.table4 = ws->d_table4.p; pp.ncls = pl->ncls; pp.gip = pl->gip; pp.gep = pl->gep; pp.has_dollar = pl->has_dollar;
+    pp.half_off = (getenv("GOTOH_B200_HALF") && atoi(getenv("GOTOH_B200_HALF")) == 0) ? 1 : 0;
+    pp.pairN = reinterpret_cast<int32_t*>(d + o_N); pp.pairLo = reinterpret_cast<int32_t*>(d + o_lo);
+    pp.present = reinterpret_cast<uint32_t*>(d + o_present); pp.scal = reinterpret_cast<int32_t*>(d + o_scal);
+    pp.acc = reinterpret_cast<unsigned long long*>(d + o_acc);
+    pp.hist = reinterpret_cast<uint32_t*>(d + o_hist); pp.cursor = reinterpret_cast<uint32_t*>(d + o_cursor);
+    pp.bin_pair = reinterpret_cast<int64_t*>(d + o_bin_pair); pp.bin_ops = reinterpret_cast<int64_t*>(d + o_bin_ops);
+    pp.grp = reinterpret_cast<int64_t*>(d + o_grp);
+    pp.summary = ws->h_prep_sum.p;
+    const int nblocks = (int)((n + 255) / 256);
+    GOTOH_LAUNCH(k_prep_scan, dim3(nblocks), dim3(256), 0, ws->stream, pp);
+    GOTOH_LAUNCH(k_prep_range, dim3(1), dim3(256), 0, ws->stream, pp);
+    GOTOH_LAUNCH(k_prep_bins, dim3(nblocks), dim3(256), 0, ws->stream, pp);
+    GOTOH_LAUNCH(k_prep_layout, dim3(1), dim3(256), 0, ws->stream, pp);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ws->ev_p, ws->stream));
+    CU(cudaEventSynchronize(ws->ev_p));
+    phase(2);
+    const PrepSummary sum = *ws->h_prep_sum.p;
+    if (sum.fallback) {
+        if (trace_on()) fprintf(stderr, "[gotoh_b200] device plan builder declined %lld pairs (reason %d): host builder\n", (long long)n, sum.fallback);
+        return GOTOH_B200_OK;
+    }
+    // ---- arena budget: one chunk or the host builder (which cuts chunks) ---------------------------------------------
+    int64_t budget = pl->arena_budget_bytes;
+    if (getenv("GOTOH_B200_ARENA_MB")) budget = (int64_t)atoll(getenv("GOTOH_B200_ARENA_MB")) << 20;
+    if (budget <= 0) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        budget = (int64_t)((free_b + ws->d_dir.cap * sizeof(uint4)) * 0.80);
+    }
+    if (sum.arena_u4 * 16 > budget) return GOTOH_B200_OK;
+    // ---- device buffers of the plan -----------------------------------------------------------------------------------------
+    pl->out_mode = pl->out_mode;
+    if (out_off) { pl->out_base = out_off[pair_begin]; pl->out_bytes = out_off[pair_end] - out_off[pair_begin]; }
+    else { pl->out_base = 0; pl->out_bytes = sum.sum_mn; }
+    CU(ws->d_pairs.ensure((size_t)n));
+    CU(ws->d_tasks.ensure((size_t)sum.n_tasks));
+    CU(ws->d_score.ensure((size_t)n)); CU(ws->d_end_i.ensure((size_t)n)); CU(ws->d_end_j.ensure((size_t)n));
+    CU(ws->d_nops.ensure((size_t)n)); CU(ws->d_i0.ensure((size_t)n)); CU(ws->d_j0.ensure((size_t)n));
+    CU(ws->d_len_plan.ensure((size_t)n)); CU(ws->d_out_len.ensure((size_t)n)); CU(ws->d_out_score.ensure((size_t)n));
+    CU(ws->d_ops.ensure((size_t)sum.ops_words));
+    if (pl->out_mode != OUT_COMPACT) {
+        CU(ws->d_out_ref.ensure((size_t)pl->out_bytes));
+        CU(ws->d_out_qry.ensure((size_t)pl->out_bytes));
+    }
+    if (pl->out_mode != OUT_STRIDED) {
+        if (pl->out_mode == OUT_TIGHT) CU(ws->d_scan_in.ensure((size_t)n));
+        CU(ws->d_scan_out.ensure((size_t)n + 1));
+    }
+    if (pl->out_mode == OUT_COMPACT) {
+        CU(ws->d_rec.ensure((size_t)n * 8));
+        CU(ws->d_cops.ensure((size_t)sum.ops_words));
+    }
+    {
+        cudaError_t e = ws->d_dir.ensure((size_t)sum.arena_u4);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return GOTOH_B200_OK; }       // the host builder cuts chunks
+    }
+    pp.pairs = ws->d_pairs.p; pp.tasks = ws->d_tasks.p;
+    GOTOH_LAUNCH(k_prep_scatter, dim3(nblocks), dim3(256), 0, ws->stream, pp);
+    CU(cudaGetLastError());
+    // ---- the plan ---------------------------------------------------------------------------------------------------------------
+    pl->chunks.clear();
+    Chunk c;
+    c.pair_first = 0; c.pair_count = (int)n;
+    for (int l = 0; l < sum.n_launch; ++l) {
+        Launch L;
+        L.x2 = 1; L.K = sum.launch[l].K; L.hw = sum.launch[l].hw;
+        L.task_first = sum.launch[l].task_first; L.task_count = sum.launch[l].task_count;
+        L.rebase_mask = sum.R - 1; L.multi_strip = 0;
+        c.launches.push_back(L);
+    }
+    pl->chunks.push_back(c);
+    pl->n_launches = (int)c.launches.size() + 2;
+    CU(ws->d_counter.ensure((size_t)pl->n_launches));
+    pl->zshift = sum.z4;
+    pl->smin_m1 = (int)((long long)std::min(sum.minT, 0) * 32 * PLAN_MAX_K - 2LL * pl->gip - pl->gep - 2);
+    pl->cells = sum.cells; pl->pairs_x2 = n; pl->pairs_x1 = 0;
+    pl->pair_base = pair_begin; pl->n_pairs = n; pl->ops_words = sum.ops_words;
+    pl->arena_bytes = sum.arena_u4 * 16;
+    pl->bnd_stride = 0; pl->flow_slots = 0; pl->n_stasks = 0;
+    phase(7);
+    pl->built_on_device = true;
+    *done = true;
+    return GOTOH_B200_OK;
+}
+
 int launch_emit(const gotoh_b200_plan* pl, int pair_first, int pair_count, const int64_t* tight_off) {
     const Workspace* ws = pl->ws;
     EmitParams ep;
@@ -1226,8 +1431,10 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     // slab = as many consecutive pairs as fit the arena estimate ((M+40)*64 B per strip per pair).  (Ramping the slab
     // size up and down to shorten the pipeline's fill and drain was tried and measured slower on B200 than equal slabs.)
     std::vector<int64_t> cuts(1, lo);
+    std::vector<double> slab_cells;                  // estimated DP cells per slab (untrimmed lengths)
     for (int64_t k = lo; k < hi;) {
         int64_t est = 0, e = k;
+        double cells = 0.0;
         while (e < hi) {
             const int64_t r = ref_idx ? ref_idx[e] : e;
             const int64_t m = (r >= 0 && r < n_refs) ? ref_off[r + 1] - ref_off[r] : 0;
@@ -1235,9 +1442,11 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
             const int64_t need = (std::max<int64_t>(nq, 1) + 255) / 256 * (m + 40) * 64;
             if (e > k && (est + need > slab_budget || e - k >= (1 << 20))) break;
             est += need;
+            cells += (double)m * (double)nq;
             ++e;
         }
         cuts.push_back(e);
+        slab_cells.push_back(cells);
         k = e;
     }
     const int nslabs = (int)cuts.size() - 1;
@@ -1291,7 +1500,10 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
                 if (failed) return;
             }
             const double t_a2 = now_ms();
-            if (cudaStreamSynchronize(pl->ws->stream) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed");
+            if (pl->ws->ev_done_pending) {
+                if (cudaEventSynchronize(pl->ws->ev_done) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "a slab's kernels or copies failed: %s", cudaGetErrorString(cudaGetLastError()));
+                pl->ws->ev_done_pending = false;
+            }
             if (trace_on() && two_phase)
                 fprintf(stderr, "[gotoh_b200] dev %d builder %d slab %d: workspace released by the collector at %.2f ms (waited %.2f), stream drained at %.2f ms\n",
                         dev, b, slab, t_a2 - t_entry, t_a2 - t_a, now_ms() - t_entry);
@@ -1307,7 +1519,17 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
             for (double& x : g_trace_phase) x = 0;
             if (!rc) {
                 try {
-                    rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, cuts[(size_t)slab], cuts[(size_t)slab + 1], out.out_off_in);
+                    // Who lays the slab out?  The device builder costs a GPU round trip - its kernels queue behind the persistent
+                    // forward CTAs of the slabs ahead, up to one forward-kernel duration (2 ms measured on C2) - the host builder
+                    // ~0.2 us of one core per pair.  Pairs with many cells (a 251-nt read against a 3 kb standard: 0.15 us of GPU
+                    // time) leave a core time to keep up; short pairs (84-aa windows: 0.009 us) do not.
+                    bool on_device = false;
+                    const double per_pair = slab_cells[(size_t)slab] / (double)std::max<int64_t>(1, cuts[(size_t)slab + 1] - cuts[(size_t)slab]);
+                    const char* sw = getenv("GOTOH_B200_DEVICE_PREP");
+                    if (sw ? atoi(sw) != 0 : per_pair < 262144.0)
+                        rc = plan_build_device(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, cuts[(size_t)slab], cuts[(size_t)slab + 1], out.out_off_in, &on_device);
+                    if (!rc && !on_device)
+                        rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, cuts[(size_t)slab], cuts[(size_t)slab + 1], out.out_off_in);
                 } catch (const std::bad_alloc&) {
                     rc = fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
                 }
@@ -1333,6 +1555,10 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
             if (trace_on()) cudaEventRecord(pl->ws->ev[1], pl->ws->stream);
             if (inject_fetch_failure && slab == 1) rc = fail(GOTOH_B200_ECUDA, "injected result-copy failure (GOTOH_B200_TEST_FAIL_FETCH)");
             if (!rc) rc = two_phase ? plan_fetch_a(pl) : plan_fetch(pl, out.out_ref, out.out_qry, out.out_len, out.out_score);
+            if (!rc && !two_phase) {
+                if (cudaEventRecord(pl->ws->ev_done, pl->ws->stream) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "cudaEventRecord failed");
+                pl->ws->ev_done_pending = true;
+            }
             if (trace_on() && !rc) { cudaEventRecord(pl->ws->ev[2], pl->ws->stream); pl->ws->trace_slab = slab; }
             if (trace_on())
                 fprintf(stderr, "[gotoh_b200] dev %d builder %d slab %d pairs %lld: wait %.1f ms, build %.1f ms (refs %.1f pass1 %.1f pass2 %.1f cls %.1f path %.1f sort %.1f tasks %.1f alloc+h2d %.1f), enqueue %.1f ms\n",
@@ -1370,6 +1596,10 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
                           (long long)(base - out.cap_lo), (long long)(out.cap_hi - out.cap_lo), out.mode == OUT_TIGHT ? "byte" : "word");
             const double t_ev = now_ms();
             if (!rc) rc = plan_fetch_b(pl, out, base, total);
+            if (!rc) {
+                if (cudaEventRecord(ws->ev_done, ws->stream) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "cudaEventRecord failed");
+                ws->ev_done_pending = true;
+            }
             if (rc) { fail_and_wake(builders, rc); return; }
             if (trace_on())
                 fprintf(stderr, "[gotoh_b200] dev %d collector slab %d: phase A seen at %.2f ms, done at %.2f ms, phase B enqueued at %.2f ms (total %lld)\n",
@@ -1396,6 +1626,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     for (int b = 0; b <= builders; ++b)
         if (rcs[(size_t)b] && !rc) rc = fail(rcs[(size_t)b], "%s", msgs[(size_t)b].c_str());
     for (int w = 0; w < nws; ++w) {
+        ctx->ws[w].ev_done_pending = false;
         const cudaError_t e = cudaStreamSynchronize(ctx->ws[w].stream);
         if (e != cudaSuccess && !rc) rc = fail(GOTOH_B200_ECUDA, "stream synchronize failed: %s", cudaGetErrorString(e));
     }
@@ -1433,7 +1664,9 @@ extern "C" int32_t gotoh_b200_plan_create(int32_t device, const uint8_t* ref_byt
     for (double& x : g_trace_phase) x = 0;
     if (!rc) {
         try {
-            rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, 0, n_pairs, out_off);
+            bool on_device = false;
+            rc = plan_build_device(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, 0, n_pairs, out_off, &on_device);
+            if (!rc && !on_device) rc = plan_build(pl, ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, 0, n_pairs, out_off);
         } catch (const std::bad_alloc&) {
             rc = fail(GOTOH_B200_ENOMEM, "out of host memory while packing");
         }
@@ -1471,6 +1704,7 @@ extern "C" int64_t gotoh_b200_plan_stat(const gotoh_b200_plan* pl, int32_t what)
         case 5: return pl->pairs_x2;
         case 6: return pl->pairs_x1;
         case 7: return (int64_t)pl->chunks.size();
+        case 8: return pl->built_on_device ? 1 : 0;
     }
     return -1;
 }
