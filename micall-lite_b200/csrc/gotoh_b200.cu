@@ -341,15 +341,25 @@ int host_threads(int64_t bytes) {
 template <class V, int K, bool MULTI, bool HALF = false>
 int launch_forward_k(const gotoh_b200_plan* pl, FwdParams fp, int ntasks) {
     const Workspace* ws = pl->ws;
-    const size_t per_warp = FwdSmem<V, K>::per_warp(pl->ncls);
+    const size_t per_warp = FwdSmem<V, K, HALF>::per_warp(pl->ncls);
     // warps per CTA: 4 unless the query profile (1 KB per class per warp at K = 8) needs more room
     int warps = FWD_WARPS;
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-    const size_t smem = per_warp * warps;
+    // half-warp kernels: a CTA-wide int16 copy of the score table for the per-task profile build, when it is small
+    // (amino-acid tables: 21 classes = 5 KB) and no stop-codon bonus applies
+    fp.stab_bytes = (HALF && !pl->has_dollar && pl->ncls <= 32) ? pl->ncls * 256 : 0;
+    const size_t smem = per_warp * warps + fp.stab_bytes;
     if (smem > 220 * 1024) return fail(GOTOH_B200_ERANGE, "profile needs %zu bytes of shared memory", smem);
     CU(cudaFuncSetAttribute((k_forward<V, K, MULTI, HALF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // persistent grid: enough CTAs to fill every SM, tasks are pulled from a counter
-    int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(GOTOH_MIN_CTAS, (200 * 1024) / std::max<size_t>(smem, 1)));
+    // persistent grid: as many CTAs as are resident at once (asked from the runtime: a 21-class amino-acid profile at K = 6
+    // takes 68 KB per CTA and three of them fit the SM's 228 KB, which a fixed 200 KB budget got wrong), tasks are pulled
+    // from a counter
+    int ctas_per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, (k_forward<V, K, MULTI, HALF>), warps * 32, smem) != cudaSuccess || ctas_per_sm < 1) {
+        (void)cudaGetLastError();
+        ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(GOTOH_MIN_CTAS, (200 * 1024) / std::max<size_t>(smem, 1)));
+    }
+    ctas_per_sm = std::min(ctas_per_sm, (int)GOTOH_MIN_CTAS);
     int grid = std::min((ntasks + warps - 1) / warps, ws->sm_count * ctas_per_sm);
     // task_limit > 0 (one-shot pipeline): CTAs retire after task_limit tasks per warp, so the short traceback / emit
     // kernels of the previous slab (other streams) get SM slots while this launch is still running
@@ -527,6 +537,8 @@ int build_refs(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64_t* ref
     CU(ws->h_table4.ensure((size_t)pl->ncls * 136));
     int32_t* h_table4 = ws->h_table4.p;           // [ncls][128] scores, then [ncls][8] bonuses
     memset(h_table4, 0, (size_t)pl->ncls * 136 * sizeof(int32_t));
+    // entry 0 of every class row (no query byte is 0): 4u, what a padding column beyond N scores
+    for (int c = 0; c < pl->ncls; ++c) h_table4[(size_t)c * 128] = -4 * pl->gip;
     for (int c = 1; c < pl->ncls; ++c) {
         for (int b = 1; b < 127; ++b) h_table4[(size_t)c * 128 + b] = 4 * (tab.v[rep[(size_t)c]][b] + 2 * pl->gep);
         for (int cm = 0; cm < 8; ++cm) {

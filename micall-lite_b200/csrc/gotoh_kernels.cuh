@@ -92,6 +92,7 @@ struct FwdParams {
     int32_t* end_j;
     uint32_t* work_counter;     // dynamic task scheduler
     // strip dataflow (k_forward_flow): tasks are (pair_a = pair, pair_b = strip); slot = pairs[pair].pad1 + strip
+    int32_t stab_bytes;         // half-warp kernels: bytes of the CTA-wide int16 copy of table4 at the start of shared memory (0: none)
     int32_t task_limit;         // 0: persistent warps drain the queue; n > 0: a warp retires after n tasks (see plan_run)
     int32_t* prog;              // rows published per slot
     int32_t* part_best;         // last-row partial maximum per slot
@@ -187,14 +188,17 @@ __device__ __forceinline__ int stop_mask(const uint8_t* b, int N, int j) {
     return (is_stop3(b, N, j - 3) ? 1 : 0) | (is_stop3(b, N, j - 2) ? 2 : 0) | (is_stop3(b, N, j - 1) ? 4 : 0);
 }
 
-template <class V, int K>
+template <class V, int K, bool LEAN = false>
 struct FwdSmem {
     enum { K4 = (K + 3) / 4, USE2 = (K == 2 || K == 6), E2 = (K + 1) / 2, ROW_BYTES = USE2 ? E2 * 8 : K4 * 16 };
     // profile: [class][K4][lane] of 4 packed entries (K = 2, 6: [class][K/2][lane] of 2 entries - no padding words, so
     // a 21-class amino-acid profile at K = 6 leaves room for 3 CTAs per SM instead of 2);
     // + a 2x32 int2 ring for multi-strip boundaries
+    // LEAN (half-warp wavefronts): + a slot of K words per lane for the lane's last-row values (kept at row M, reduced once,
+    // uniformly, after the strip instead of inside a divergent branch)
+    enum { SLOT_BYTES = LEAN ? K * 32 * 4 : 0 };
     static __host__ __device__ size_t prof_bytes(int ncls) { return (size_t)ncls * ROW_BYTES * 32; }
-    static __host__ __device__ size_t per_warp(int ncls) { return prof_bytes(ncls) + 2 * 32 * sizeof(int2); }
+    static __host__ __device__ size_t per_warp(int ncls) { return prof_bytes(ncls) + 2 * 32 * sizeof(int2) + SLOT_BYTES; }
 };
 
 // State of one warp sweeping one strip (32*K query columns) down the reference.
@@ -224,10 +228,16 @@ template <class T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldc
 // (pair, strip) is its own warp task; strip s publishes its last column to global memory every 32 rows and strip
 // s+1 - on any warp of any CTA - follows ~64 rows behind.  Tasks are claimed from an atomic counter in (pair, strip)
 // order, so a strip's producer is always claimed earlier and is running: the spin-waits cannot deadlock.
-template <class V, int K, int MODE>
+// LEAN (single strip, short tasks: the half-warp kernels, where fill and drain are 10-30 % of a task): rows above the
+// reference run on the padding class and leave the row-0 state untouched (no re-initialisation), the last-row values are
+// kept in shared memory and reduced after the strip.  The other instantiations keep the plain form (re-initialise at row
+// 0, reduce the last row in place): their tasks are hundreds of blocks long and ptxas schedules their FAST body - which
+// runs at the 128-register cap - measurably better without the extra code (A/B on B200, C2: 142.5 vs 147.4 ms).
+template <class V, int K, int MODE, bool LEAN = false>
 struct Wave {
     typedef typename V::T T;
     enum { K4 = (K + 3) / 4, USE2 = (K == 2 || K == 6), E2 = (K + 1) / 2, STEPS = V::STEPS, NP = V::NPAIR, MULTI = (MODE != 0), CTA = (MODE == 2), FLOW = (MODE == 3), XR = 256 };
+    static_assert(!LEAN || MODE == 0, "LEAN is a single-strip form");
 
     // ---- per-task / per-strip constants --------------------------------------------------
     int lane, M, Na, Nb, j0, strip, gep, g4, rebase_mask, smin_m1, z4;
@@ -237,6 +247,8 @@ struct Wave {
     const uint8_t* cls;            // cls[i-1] = class of reference row i
     const uint8_t* clsl;           // cls - lane: clsl[t] is the class of row t - lane + 1 (one add per block, not per step)
     int2* ring;
+    int slot_off, warp_bytes;      // LEAN, CTA-uniform: byte offset of warp 0's slot area in dynamic shared memory, bytes per warp (the
+                                   // slot address is recomputed where it is needed instead of living in a register)
     const int2* bnd_in;
     int2* bnd_out;
     // MODE 2: rings of XR rows in shared memory + published/consumed row sequence numbers
@@ -272,6 +284,19 @@ struct Wave {
     int next_cls;
     uint4 dwords;
 
+    // this lane's first slot word (stride 32 words): see FwdSmem::SLOT_BYTES
+    __device__ __forceinline__ unsigned* slot_ptr() const {
+        GOTOH_DYN_SMEM(smem_all);
+        return reinterpret_cast<unsigned*>(smem_all + slot_off + (int)(threadIdx.x >> 5) * warp_bytes) + (threadIdx.x & 31);
+    }
+    // the last-column tracker's seed (row 0)
+    __device__ __forceinline__ T best_seed() const {
+        // (Vec16: every stored value of an admitted pair is >= 0 after the shift, so a stored 0 carried to column N is below
+        // all of them - real values win ties - and, unlike the plan-wide bound smin_m1, always fits 16 bits)
+        if (NP == 2) return V::pack(Na * g4, Nb * g4);
+        return V::pack(4 * smin_m1 + Na * g4, 4 * smin_m1 + Nb * g4);
+    }
+
     // S(0,j) = 0 and P(0,j) = 0 (gotoh.cpp:267-272) in the frame: 4*j*g (+1 tag for P); padding
     // columns (j > N) clone column N so that S[K-1] of the owner lane always reads S^(i,N).
     __device__ __forceinline__ void row0_init() {
@@ -283,11 +308,7 @@ struct Wave {
         }
         Sd_in = V::pack(min(j0, Na) * g4 + z4, min(j0, Nb) * g4 + z4);   // S^(0, j0)
         diag0 = lane == 0 ? V::both(z4) : V::both(0);           // 4*(i-1)*g at i = 1 (stays 0 outside lane 0)
-        // seed below any reachable score, expressed in the row-0 frame of column N
-        // (Vec16: every stored value of an admitted pair is >= 0 after the shift, so -4 is below all of them and, unlike
-        // the plan-wide bound smin_m1, always fits 16 bits)
-        if (NP == 2) best = V::pack(Na * g4, Nb * g4);          // = a stored 0 carried to column N: real values win ties
-        else best = V::pack(4 * smin_m1 + Na * g4, 4 * smin_m1 + Nb * g4);
+        best = best_seed();
         best_i_a = best_i_b = lane;                              // row 0
     }
 
@@ -435,21 +456,59 @@ struct Wave {
         }
 
         if (SLOW) {
-            // row 0: re-initialise the lane just before its first real row
-            if (i == 0) row0_init();
-            // row M: last-row maximum over this lane's real columns
-            if (i == M) {
-                const int roff = (NP == 2) ? (M & rebase_mask) : M;   // i - base(i)
+            if (LEAN) {
+                // Row 0.  While the wavefront fills, a lane runs on the rows above the reference: padding class 0, whose profile
+                // entries are 0 (real columns) / 4u (padding columns).  That leaves S^ and P^ exactly at their row-0 values:
+                // P^' = max(S^ + 4u+1, P^) = P^ (P^ = S^+1), D^ = S^(j-1) + 0 and Q^ <= S^(j-1) + 4u+2 are both below P^ (or,
+                // with gip = gep = 0, clear to the same S^), so C = P^ and S^' = clr(C) = S^; the left neighbour is above the
+                // reference too and hands over the same constants (its first hand-over is preset to them).  Only the
+                // last-column tracker ran ahead: it gets its seed back.
+                const bool z = (i == 0);
+                best = z ? best_seed() : best;
+                best_i_a = z ? t : best_i_a;
+                if (NP == 2) best_i_b = z ? t : best_i_b;
+                // row M: keep the lane's last-row values; lastrow_finish() reduces them after the strip (gotoh.cpp:399-403)
+                if (i == M) {
+                    unsigned* slot = slot_ptr();
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int j = j0 + k + 1;
-                    const int sa = ((V::lo(S[k]) - z4) >> 2) - (roff + j) * gep;
-                    if (j <= Na && sa >= lr_best_a) { lr_best_a = sa; lr_j_a = j; }
-                    if (NP == 2) {
-                        const int sb = ((V::hi(S[k]) - z4) >> 2) - (roff + j) * gep;
-                        if (j <= Nb && sb >= lr_best_b) { lr_best_b = sb; lr_j_b = j; }
+                    for (int k = 0; k < K; ++k) slot[k * 32] = V::raw(S[k]);
+                }
+            } else {
+                // row 0: re-initialise the lane just before its first real row
+                if (i == 0) row0_init();
+                // row M: last-row maximum over this lane's real columns
+                if (i == M) {
+                    const int roff = (NP == 2) ? (M & rebase_mask) : M;   // i - base(i)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int j = j0 + k + 1;
+                        const int sa = ((V::lo(S[k]) - z4) >> 2) - (roff + j) * gep;
+                        if (j <= Na && sa >= lr_best_a) { lr_best_a = sa; lr_j_a = j; }
+                        if (NP == 2) {
+                            const int sb = ((V::hi(S[k]) - z4) >> 2) - (roff + j) * gep;
+                            if (j <= Nb && sb >= lr_best_b) { lr_best_b = sb; lr_j_b = j; }
+                        }
                     }
                 }
+            }
+        }
+    }
+
+    // Last-row maximum over this lane's real columns of the strip, from the values kept at row M (larger j wins ties).
+    // Uniform code, once per strip (it used to run inside the divergent `i == M` branch of 16-32 consecutive steps).
+    __device__ __forceinline__ void lastrow_finish() {
+        if (!LEAN) return;
+        const int roff = (NP == 2) ? (M & rebase_mask) : M;   // i - base(i) at i = M
+        const unsigned* slot = slot_ptr();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const T sk = (T)slot[k * 32];
+            const int j = j0 + k + 1;
+            const int sa = ((V::lo(sk) - z4) >> 2) - (roff + j) * gep;
+            if (j <= Na && sa >= lr_best_a) { lr_best_a = sa; lr_j_a = j; }
+            if (NP == 2) {
+                const int sb = ((V::hi(sk) - z4) >> 2) - (roff + j) * gep;
+                if (j <= Nb && sb >= lr_best_b) { lr_best_b = sb; lr_j_b = j; }
             }
         }
     }
@@ -501,14 +560,23 @@ template <class V, int K, bool MULTI, bool HALF = false>
 __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(const FwdParams p) {
     static_assert(!HALF || (V::NPAIR == 2 && !MULTI), "HALF is a single-strip int16x2 mode");
     typedef typename V::T T;
-    typedef Wave<V, K, MULTI ? 1 : 0> W;
+    typedef Wave<V, K, MULTI ? 1 : 0, HALF> W;
+    typedef FwdSmem<V, K, HALF> SM;
     enum { K4 = W::K4, STEPS = V::STEPS, NP = V::NPAIR, FILL = HALF ? 15 : 31 };
     GOTOH_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, plane = threadIdx.x & 31;
     const int lane = HALF ? (plane & 15) : plane;       // lane within its wavefront
     const int sub = HALF ? (plane >> 4) : 0;
-    unsigned char* my_smem = smem_raw + (size_t)warp * FwdSmem<V, K>::per_warp(p.ncls);
+    unsigned char* my_smem = smem_raw + p.stab_bytes + (size_t)warp * SM::per_warp(p.ncls);
     uint4* prof = reinterpret_cast<uint4*>(my_smem);
+    // half-warp kernels rebuild the query profile every 100-440 rows: the score table comes from a CTA-wide int16 copy in
+    // shared memory (32-bit addresses with immediate offsets instead of a 64-bit address per global load)
+    const short* stab = reinterpret_cast<const short*>(smem_raw);
+    if (HALF && p.stab_bytes) {
+        short* st = reinterpret_cast<short*>(smem_raw);
+        for (int x = threadIdx.x; x < p.ncls * 128; x += blockDim.x) st[x] = (short)p.table4[x];
+        __syncthreads();
+    }
 
     W w;
     w.lane = lane;
@@ -520,7 +588,9 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
     w.one = p.four >> 2;
     w.z4 = (NP == 2) ? p.zshift : 0;
     w.prof_lane = W::USE2 ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint2*>(prof) + plane) : prof + plane;
-    w.ring = reinterpret_cast<int2*>(my_smem + FwdSmem<V, K>::prof_bytes(p.ncls));  // [2][32]
+    w.ring = reinterpret_cast<int2*>(my_smem + SM::prof_bytes(p.ncls));  // [2][32]
+    w.slot_off = p.stab_bytes + (int)(SM::prof_bytes(p.ncls) + 2 * 32 * sizeof(int2));
+    w.warp_bytes = (int)SM::per_warp(p.ncls);
     const int u4 = -4 * p.gip;
     w.c_up = V::both(u4 + 1);          // P^ = max(S^up + 4u+1, P^up)
     w.c_sl0 = V::both(u4 + w.z4);          // column 0 seen by the Q recurrence: s~ = u   (gotoh.cpp:291)
@@ -592,6 +662,23 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
                 qca[k] = ja < Na ? (int)qa[ja] : -1;
                 qcb[k] = (NP == 2 && ja < Nb) ? (int)qb[ja] : -1;
             }
+            if (HALF && p.stab_bytes) {
+                // Column-major build from the shared-memory table (short queries rebuild the profile every 100-440 rows, so
+                // its cost counts: it was 8 % of the C3 kernel's instructions): per column two 32-bit table offsets, per
+                // class two 16-bit loads, one multiply-add and one 32-bit store - no per-entry conditions, because padding
+                // columns read entry 0 of the class row, which the host sets to 4u (the value that makes them clone
+                // column N).
+                unsigned* profw = reinterpret_cast<unsigned*>(prof);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const short* ta = stab + (qca[k] >= 0 ? qca[k] : 0);
+                    const short* tb = stab + (qcb[k] >= 0 ? qcb[k] : 0);
+                    unsigned* dw = profw + (W::USE2 ? ((k >> 1) * 32 + plane) * 2 + (k & 1) : ((k >> 2) * 32 + plane) * 4 + (k & 3));
+                    const int cstride = W::USE2 ? W::E2 * 64 : K4 * 128;        // 32-bit words per class row
+#pragma unroll 7
+                    for (int c = 0; c < p.ncls; ++c) dw[c * cstride] = V::lin((int)ta[c * 128], (int)tb[c * 128]);
+                }
+            } else
             for (int c = 0; c < p.ncls; ++c) {
                 const int32_t* trow = p.table4 + c * 128;
                 const int32_t* brow = p.bonus4 + c * 8;
@@ -623,24 +710,47 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
             }
             __syncwarp();
 
-            w.sendS = V::both(0);
-            w.sendQ = V::both(0);
             w.dwords = make_uint4(0, 0, 0, 0);
             w.row0_init();                              // lane 0 starts at row 1 in the very first step
+            // what the right neighbour consumes in the first step: it is above the reference then and must see this lane's
+            // row-0 constants (see step(): rows above the reference leave the row-0 state untouched)
+            w.sendS = HALF ? w.S[K - 1] : V::both(0);
+            w.sendQ = HALF ? V::add(w.S[K - 1], V::both(u4 + 2)) : V::both(0);
             w.next_cls = w.cls[-lane];                  // class of row i = 1 - lane (padding when i < 1)
 
+            // Which per-lane events can occur in the steps t0 .. hi of a block (rows t-FILL .. t)?  Row 0 (re-init) in the
+            // blocks with t0 <= FILL, row M (capture, i <= M guard) in those with hi >= M, a rebase row (int16x2) in those
+            // that meet [m, m+FILL] for a multiple m of R: these run the SLOW body.
             uint4* dst = p.dir + pa.dir_off + (int64_t)strip * nblk * 32 + plane;
-            for (int tb = 0; tb < nblk; ++tb, dst += 32) {
-                // Which per-lane events can occur in steps t0 .. hi of this block (rows t-31 .. t)?
-                const int t0 = tb * STEPS + 1, hi = t0 + STEPS - 1;
-                bool slow = (t0 <= FILL) || (hi >= M);                    // row 0 re-init / row M capture, i <= M
-                if (NP == 2) {
-                    const int m = hi & ~p.rebase_mask;                  // largest multiple of R that is <= hi
-                    slow = slow || (m > 0 && m >= t0 - FILL);             // some lane crosses a rebase row
+            int tb = 0;
+            if (!HALF) {
+                // 32-lane wavefronts: one loop with a per-block test (their tasks are hundreds of blocks long)
+                for (; tb < nblk; ++tb, dst += 32) {
+                    const int t0 = tb * STEPS + 1, hi = t0 + STEPS - 1;
+                    bool slow = (t0 <= FILL) || (hi >= M);                    // row 0 re-init / row M capture, i <= M
+                    if (NP == 2) {
+                        const int m = hi & ~p.rebase_mask;                  // largest multiple of R that is <= hi
+                        slow = slow || (m > 0 && m >= t0 - FILL);             // some lane crosses a rebase row
+                    }
+                    if (slow) w.template block<true>(tb, dst);
+                    else w.template block<false>(tb, dst);
                 }
-                if (slow) w.template block<true>(tb, dst);
-                else w.template block<false>(tb, dst);
+            } else {
+                // half-warp wavefronts (tasks of 25-115 blocks, 9 of them SLOW): the loop is cut into phases so that the FAST
+                // blocks in between carry no classification at all
+                const int head = min(nblk, (FILL - 1) / STEPS + 1);                 // blocks with t0 = tb*STEPS+1 <= FILL
+                const int tail = max(head, min(nblk, (M + STEPS - 1) / STEPS - 1));  // first block with hi = (tb+1)*STEPS >= M
+                for (; tb < head; ++tb, dst += 32) w.template block<true>(tb, dst);
+                const int R = p.rebase_mask + 1;
+                for (int m = R; tb < tail; m += R) {
+                    const int rb0 = min(tail, max(tb, (m - 1) / STEPS));          // block that holds step m
+                    const int rb1 = min(tail, max(rb0, (m + FILL - 1) / STEPS + 1));  // one past the block that holds step m+FILL
+                    for (; tb < rb0; ++tb, dst += 32) w.template block<false>(tb, dst);
+                    for (; tb < rb1; ++tb, dst += 32) w.template block<true>(tb, dst);
+                }
+                for (; tb < nblk; ++tb, dst += 32) w.template block<true>(tb, dst);
             }
+            w.lastrow_finish();
         }
 
         // ---- K3 epilogue: end-cell choice (gotoh.cpp:418-450) -----------------------------
@@ -707,6 +817,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_flow
     w.z4 = 0;
     w.prof_lane = prof + lane;
     w.ring = reinterpret_cast<int2*>(my_smem + (size_t)p.ncls * K4 * 32 * 16);
+    w.slot_off = 0; w.warp_bytes = 0;
     const int u4 = -4 * p.gip;
     w.c_up = V::both(u4 + 1);
     w.c_sl0 = V::both(u4);
@@ -780,6 +891,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_flow
             if (slow) w.template block<true>(tb, dst);
             else w.template block<false>(tb, dst);
         }
+        w.lastrow_finish();
         // last row of this strip: (score, j) with larger j winning ties (gotoh.cpp:399-403)
         int lr_best = w.lr_best_a, lr_j = w.lr_j_a;
 #pragma unroll
@@ -839,7 +951,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_cta(
     __shared__ int sh_lr_best[FWD_WARPS], sh_lr_j[FWD_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t prof_bytes = (size_t)p.ncls * K4 * 32 * 16;
-    unsigned char* my_smem = smem_raw + (size_t)warp * (prof_bytes + XR * sizeof(int2));
+    const size_t warp_bytes = prof_bytes + XR * sizeof(int2);
+    unsigned char* my_smem = smem_raw + (size_t)warp * warp_bytes;
     uint4* prof = reinterpret_cast<uint4*>(my_smem);
 
     W w;
@@ -866,7 +979,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_cta(
     w.inj_q = lane == 0 ? V::raw(w.c_q0) : 0u;
     const int pw = (warp + FWD_WARPS - 1) % FWD_WARPS;      // the warp that produces my left boundary
     w.xout = reinterpret_cast<int2*>(my_smem + prof_bytes);
-    w.xin = reinterpret_cast<const int2*>(smem_raw + (size_t)pw * (prof_bytes + XR * sizeof(int2)) + prof_bytes);
+    w.xin = reinterpret_cast<const int2*>(smem_raw + (size_t)pw * warp_bytes + prof_bytes);
+    w.slot_off = 0; w.warp_bytes = 0;
     w.pub_out = &sh_pub[warp];
     w.cons_out = &sh_cons[warp];
     w.pub_in = &sh_pub[pw];
@@ -942,6 +1056,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_cta(
                 if (slow) w.template block<true>(tb, dst);
                 else w.template block<false>(tb, dst);
             }
+            w.lastrow_finish();
             // everything of the left boundary has been consumed
             if (strip > 0 && lane == 0) *w.cons_in = w.seq_in + M;
             __syncwarp();
