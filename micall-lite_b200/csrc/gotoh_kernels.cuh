@@ -284,6 +284,14 @@ struct Wave {
     int next_cls;
     uint4 dwords;
 
+    // column-0 injection constants of this lane for the strip it is about to sweep (multi-strip forms call it per strip)
+    __device__ __forceinline__ void set_injection(bool first_strip) {
+        const bool inj = (lane == 0) && first_strip;
+        c_g4_lane0 = inj ? c_g4 : V::both(0);
+        keep = one - (inj ? 1u : 0u);                 // opaque (one is a run-time 1) so x*keep stays an IMAD
+        inj_s = inj ? V::raw(c_sl0) : 0u;
+        inj_q = inj ? V::raw(c_q0) : 0u;
+    }
     // this lane's first slot word (stride 32 words): see FwdSmem::SLOT_BYTES
     __device__ __forceinline__ unsigned* slot_ptr() const {
         GOTOH_DYN_SMEM(smem_all);
@@ -332,37 +340,40 @@ struct Wave {
                                              : *reinterpret_cast<const volatile long long*>(&xin[t & (XR - 1)]);
                 Sl = (T)(int)(raw & 0xffffffffLL); Ql = (T)(int)(raw >> 32);
             }
-        } else if (MULTI && strip > 0) {
-            // boundary column written by the previous strip; staged 32 rows at a time
-            if (((t - 1) & 31) == 0) {
-                __syncwarp();
-                const int row = t + lane;                   // lane 0 is at row t+l at step t+l
-                int2 b = make_int2(0, 0);
-                if (FLOW) {
-                    b = nextb;
-                    const bool real_row = (row >= 1 && row <= M);
-                    for (;;) {
-                        const bool miss = real_row && b.x == -1;
-                        if (!__any_sync(0xffffffffu, miss)) break;
-                        if (miss) b = ld_cg(&bnd_in[row]);
-                        gotoh_pause();
-                    }
-                    const int row2 = row + 32;              // next window, consumed 32 steps from now
-                    nextb = (row2 >= 1 && row2 <= M) ? ld_cg(&bnd_in[row2]) : make_int2(0, 0);
-                } else if (row >= 1 && row <= M) b = bnd_in[row];
-                ring[(((t - 1) >> 5) & 1) * 32 + lane] = b;
-                __syncwarp();
-            }
-            if (lane == 0) {
-                const int2 b = ring[(((t - 1) >> 5) & 1) * 32 + ((t - 1) & 31)];
-                Sl = (T)b.x; Ql = (T)b.y;
-            }
         } else {
-            // column 0 (gotoh.cpp:290-293) is injected into lane 0.  Written as x*keep + inj (keep = 0 for
-            // lane 0, 1 elsewhere; inj = 0 outside lane 0) so that it issues as IMAD on the FMA pipe
-            // instead of three selects on the saturated ALU pipe.
+            if (MULTI && !CTA) {
+                // boundary column written by the previous strip; staged 32 rows at a time
+                if (strip > 0 && ((t - 1) & 31) == 0) {
+                    __syncwarp();
+                    const int row = t + lane;                   // lane 0 is at row t+l at step t+l
+                    int2 b = make_int2(0, 0);
+                    if (FLOW) {
+                        b = nextb;
+                        const bool real_row = (row >= 1 && row <= M);
+                        for (;;) {
+                            const bool miss = real_row && b.x == -1;
+                            if (!__any_sync(0xffffffffu, miss)) break;
+                            if (miss) b = ld_cg(&bnd_in[row]);
+                            gotoh_pause();
+                        }
+                        const int row2 = row + 32;              // next window, consumed 32 steps from now
+                        nextb = (row2 >= 1 && row2 <= M) ? ld_cg(&bnd_in[row2]) : make_int2(0, 0);
+                    } else if (row >= 1 && row <= M) b = bnd_in[row];
+                    ring[(((t - 1) >> 5) & 1) * 32 + lane] = b;
+                    __syncwarp();
+                }
+                // lane 0 takes its left neighbour from the ring - in every strip, so that the steps carry no branch on the
+                // strip number: in strip 0 what it reads is overridden by the column-0 injection below (keep = 0)
+                if (lane == 0) {
+                    const int2 b = ring[(((t - 1) >> 5) & 1) * 32 + ((t - 1) & 31)];
+                    Sl = (T)b.x; Ql = (T)b.y;
+                }
+            }
+            // column 0 (gotoh.cpp:290-293) is injected into lane 0 of strip 0.  Written as x*keep + inj (keep = 0 for that
+            // lane, 1 elsewhere; inj = 0 elsewhere) so that it issues as IMAD on the FMA pipe instead of three selects on
+            // the saturated ALU pipe; in the later strips of a multi-strip pair keep = 1 and inj = 0 for every lane.
 #ifdef GOTOH_LANE0_SEL
-            if (lane == 0) { Sl = c_sl0; Ql = c_q0; sdiag = diag0; }
+            if (lane == 0 && strip == 0) { Sl = c_sl0; Ql = c_q0; sdiag = diag0; }
 #else
             Sl = (T)(V::raw(Sl) * keep + inj_s);
             Ql = (T)(V::raw(Ql) * keep + inj_q);
@@ -418,7 +429,7 @@ struct Wave {
         }
         sendS = S[K - 1];
         sendQ = q;
-        if (!MULTI || strip == 0) diag0 = V::addlin(diag0, one, c_g4_lane0);   // >= 0 in the shifted frame: an IMAD
+        diag0 = V::addlin(diag0, one, c_g4_lane0);   // >= 0 in the shifted frame: an IMAD (c_g4_lane0 = 0 outside lane 0 of strip 0)
 
         // ---- directions: 2K bits per alignment per lane-step -------------------------------------
         const unsigned dstep = accC - accS;
@@ -446,7 +457,8 @@ struct Wave {
             }
         }
         // ---- boundary column for the next strip --------------------------------------------------
-        if (MULTI && !last_strip && lane == 31 && i >= 1 && i <= M) {
+        // (FAST blocks: every lane is on a real row, no range test)
+        if (MULTI && !last_strip && lane == 31 && (!SLOW || (i >= 1 && i <= M))) {
             if (CTA) {
                 const long long v = (long long)(((unsigned long long)V::raw(q) << 32) | V::raw(S[K - 1]));
                 if (out_col) *reinterpret_cast<volatile long long*>(&col[i]) = v;
@@ -631,6 +643,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
             w.j0 = j0;
             w.last_strip = (strip == nstrips - 1);
             if (MULTI) {
+                w.set_injection(strip == 0);
                 w.bnd_in = bnd0 + (int64_t)((strip + 1) & 1) * p.bnd_stride;
                 w.bnd_out = bnd0 + (int64_t)(strip & 1) * p.bnd_stride;
             }
@@ -853,6 +866,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward_flow
         w.bnd_in = p.bnd + (int64_t)(slot - 1) * p.bnd_stride;
         w.bnd_out = p.bnd + (int64_t)slot * p.bnd_stride;
         w.nextb = make_int2(-1, -1);                  // nothing prefetched yet: the first window is fetched on demand
+        w.set_injection(strip == 0);
 
         __syncwarp();
 #pragma unroll
