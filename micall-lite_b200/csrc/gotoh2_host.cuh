@@ -14,10 +14,11 @@ struct G2Events {
     cudaEvent_t e[5] = {0, 0, 0, 0, 0};
     bool ok = false;
     bool create() {
+        if (ok) return true;
         for (auto& x : e) if (cudaEventCreate(&x) != cudaSuccess) return false;
         return ok = true;
     }
-    ~G2Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+    void destroy() { for (auto& x : e) if (x) { cudaEventDestroy(x); x = 0; } ok = false; }
 };
 
 struct G2Bufs {
@@ -40,9 +41,14 @@ struct G2Bufs {
     }
 };
 
+// Per device, kept between calls: the grow-only buffers, the timing events and the SM count.  A single
+// Aligner.align() call is a batch of one: it must not pay for cudaGetDeviceProperties (milliseconds), cudaMemGetInfo
+// (occasionally tens of ms), event creation or cudaMalloc - measured on B200: 17.6 ms -> well under 1 ms per call.
 struct G2Cache {
     std::mutex mu;
     G2Bufs bufs;
+    G2Events ev;
+    int sm_count = 0;
 };
 std::mutex g2_cache_mu;
 G2Cache* g2_cache[64] = {nullptr};
@@ -54,7 +60,7 @@ G2Cache* g2_cache_for(int dev) {
 void g2_release_cache() {
     std::lock_guard<std::mutex> lk(g2_cache_mu);
     for (int d = 0; d < 64; ++d)
-        if (g2_cache[d]) { std::lock_guard<std::mutex> lk2(g2_cache[d]->mu); g2_cache[d]->bufs.release_all(); }
+        if (g2_cache[d]) { std::lock_guard<std::mutex> lk2(g2_cache[d]->mu); g2_cache[d]->bufs.release_all(); g2_cache[d]->ev.destroy(); }
 }
 
 struct G2Run {
@@ -231,11 +237,25 @@ int g2_run_fast(G2Bufs& b, G2Run& run, std::vector<PairInfo>& pairs) {
     const char* g2sel = getenv("GOTOH_B200_GOTOH2");
     const bool use_x2 = !run.score_only && !(g2sel && !strcmp(g2sel, "x1"));
     // ---- geometry per pair: K columns per lane, strips, blocks; chunks by arena budget ----------------------
+    // the arena budget comes from cudaMemGetInfo - which now and then takes tens of ms - only when the planes cached from
+    // earlier calls cannot hold this batch in one chunk
+    int64_t total_need = 0;
+    for (size_t k = 0; k < n; ++k) {
+        int K = 8;
+        for (int x : kK) if (32 * x >= pairs[k].N) { K = x; break; }
+        total_need += (((int64_t)pairs[k].N + 32 * K - 1) / (32 * K)) * ((pairs[k].M + 31 + FSTEPS - 1) / FSTEPS) * 32;
+    }
     size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    int64_t budget = (int64_t)(free_b * 0.7) / 32;           // in uint4 per plane pair (two planes)
-    if (getenv("GOTOH_B200_ARENA_MB")) budget = ((int64_t)atoll(getenv("GOTOH_B200_ARENA_MB")) << 20) / 32;
-    if (run.score_only) budget = (int64_t)1 << 60;
+    int64_t budget;
+    const int64_t cached = (int64_t)std::min(b.lo.cap, b.hi.cap);
+    if (run.score_only) { budget = (int64_t)1 << 60; free_b = (size_t)1 << 60; }
+    else if (!getenv("GOTOH_B200_ARENA_MB") && total_need <= cached) { budget = cached; free_b = (size_t)1 << 60; }
+    else {
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        free_b += (size_t)cached * 32;                       // what the cached planes hold is available to this call too
+        budget = (int64_t)(free_b * 0.7) / 32;               // in uint4 per plane pair (two planes)
+        if (getenv("GOTOH_B200_ARENA_MB")) budget = ((int64_t)atoll(getenv("GOTOH_B200_ARENA_MB")) << 20) / 32;
+    }
     std::vector<Extra> extra(n);
     struct Chunk { int first, count; int64_t slots, bnd; };
     std::vector<Chunk> chunks;
@@ -544,13 +564,16 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
 
     // ---- device ---------------------------------------------------------------------------------
     CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
     // grow-only device buffers, cached per device between calls (gotoh_b200_release_cache frees them): a call on a
     // few hundred pairs must not pay for cudaMalloc/cudaFree of the tie-bit arena
     G2Cache* cache = g2_cache_for(device);
     if (!cache) return fail(GOTOH_B200_ENOMEM, "out of host memory");
     std::lock_guard<std::mutex> cache_lock(cache->mu);
+    if (cache->sm_count <= 0) {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        cache->sm_count = prop.multiProcessorCount;
+    }
     G2Bufs& b = cache->bufs;
     const size_t n = (size_t)n_pairs;
     const int64_t out_bytes = score_only ? 0 : out_off[n_pairs] - out_off[0];
@@ -569,8 +592,9 @@ int g2_align_batch(int device, const uint8_t* s1_bytes, const int64_t* s1_off, i
 
     G2Run run;
     run.n = n_pairs; run.l = l; run.gop = gop; run.gep = gep; run.is_global = is_global ? 1 : 0;
-    run.score_only = score_only; run.sm_count = prop.multiProcessorCount; run.max_rows = max_rows; run.h_dmat = matrix;
-    if (!run.ev.create()) return fail(GOTOH_B200_ECUDA, "cudaEventCreate failed");
+    run.score_only = score_only; run.sm_count = cache->sm_count; run.max_rows = max_rows; run.h_dmat = matrix;
+    if (!cache->ev.create()) return fail(GOTOH_B200_ECUDA, "cudaEventCreate failed");
+    run.ev = cache->ev;
     const char* force = getenv("GOTOH_B200_GOTOH2");          // tests: "general" pins the un-tuned kernels (still a GPU path)
     const bool fast = gop >= 0 && gep >= 0 && !(force && !strcmp(force, "general"));
     if (score_only && !fast) return fail(GOTOH_B200_ERANGE, "score-only mode needs non-negative penalties");

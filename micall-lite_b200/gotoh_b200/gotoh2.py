@@ -71,8 +71,10 @@ class Aligner:
         uniq, s1_idx = {}, np.zeros(len(pairs), np.int32)
         for k, (a, _) in enumerate(pairs):
             s1_idx[k] = uniq.setdefault(a, len(uniq))
-        s1 = [self.clean_sequence(a) for a in uniq]
-        s2 = [self.clean_sequence(b) for _, b in pairs]
+        # the library cleans the bytes itself (ASCII upper-case, non-alphabet -> '?', gotoh2.py:70-72); only non-ASCII text
+        # goes through the reference's regular expression here, because it works on characters, not on UTF-8 bytes
+        s1 = [a if a.isascii() else self.clean_sequence(a) for a in uniq]
+        s2 = [b if b.isascii() else self.clean_sequence(b) for _, b in pairs]
         b1, o1 = packing.pack(s1, "seq1")
         b2, o2 = packing.pack(s2, "seq2")
         n = len(pairs)

@@ -18,21 +18,62 @@ from .gotoh2 import Aligner
 GAP_OPEN, GAP_EXTEND = 15, 3
 
 
-def distance_batch(pairs, library=None, device=0):
-    """[(a, b), ...] -> [Levenshtein.distance(a, b), ...] (remap.py:250) in one device call."""
-    pairs = list(pairs)
-    if not pairs:
-        return []
-    lib = library or _ffi.default_library()
-    a, ao = packing.pack([p[0] for p in pairs], "a")
-    b, bo = packing.pack([p[1] for p in pairs], "b")
-    out = np.zeros(len(pairs), np.int32)
+def _code_points(x):
+    if isinstance(x, str):
+        return np.frombuffer(x.encode("utf-32-le"), dtype=np.uint32)
+    return np.frombuffer(bytes(x), dtype=np.uint8).astype(np.uint32)
+
+
+def _dense_pair(a, b):
+    """Edit distance only asks whether two symbols are equal: the symbols the two strings share become codes 1..k, every
+    other symbol of ``a`` code 29 and of ``b`` code 30 (they match nothing on the other side).  Works on characters, so
+    'h\u00e9llo' vs 'hello' is one substitution like in python-Levenshtein, whatever the UTF-8 byte lengths."""
+    ua, ub = _code_points(a), _code_points(b)
+    common = np.intersect1d(ua, ub)
+    if len(common) > 28:
+        raise ValueError("distance(): the two strings share %d distinct symbols; this kernel handles up to 28" % len(common))
+
+    def enc(u, other):
+        if len(common) == 0 or len(u) == 0:
+            return np.full(len(u), other, dtype=np.uint8)
+        i = np.minimum(np.searchsorted(common, u), len(common) - 1)
+        return np.where(common[i] == u, i + 1, other).astype(np.uint8)
+    return enc(ua, 29), enc(ub, 30)
+
+
+def _device_distances(lib, a_list, b_list, device):
+    a, ao = packing.pack(a_list, "a")
+    b, bo = packing.pack(b_list, "b")
+    out = np.zeros(len(a_list), np.int32)
     if a.size == 0:
         a = np.zeros(1, np.uint8)
     if b.size == 0:
         b = np.zeros(1, np.uint8)
-    lib.check(lib.lib.gotoh_b200_edit_distance_batch(a.ctypes.data, ao.ctypes.data, b.ctypes.data, bo.ctypes.data,
-                                                     len(pairs), out.ctypes.data, int(device)))
+    rc = lib.lib.gotoh_b200_edit_distance_batch(a.ctypes.data, ao.ctypes.data, b.ctypes.data, bo.ctypes.data,
+                                                len(a_list), out.ctypes.data, int(device))
+    return rc, out
+
+
+def distance_batch(pairs, library=None, device=0):
+    """[(a, b), ...] -> [Levenshtein.distance(a, b), ...] (remap.py:250) in one device call.
+
+    ASCII batches with at most 30 distinct symbols on both sides (every nucleotide / amino-acid batch) go to the device
+    as they are.  Anything else - non-ASCII text, or a batch that mixes alphabets - is re-coded pair by pair first
+    (``_dense_pair``), which keeps the drop-in contract for arbitrary strings as long as one PAIR shares at most 28
+    distinct symbols."""
+    pairs = list(pairs)
+    if not pairs:
+        return []
+    lib = library or _ffi.default_library()
+    ascii_only = all((isinstance(x, str) and x.isascii()) or isinstance(x, (bytes, bytearray)) for p in pairs for x in p[:2])
+    if ascii_only:
+        rc, out = _device_distances(lib, [p[0] for p in pairs], [p[1] for p in pairs], device)
+        if rc != _ffi.ERANGE:
+            lib.check(rc)
+            return [int(x) for x in out]
+    coded = [_dense_pair(p[0], p[1]) for p in pairs]
+    rc, out = _device_distances(lib, [c[0].tobytes() for c in coded], [c[1].tobytes() for c in coded], device)
+    lib.check(rc)
     return [int(x) for x in out]
 
 

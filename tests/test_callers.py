@@ -92,8 +92,9 @@ def test_emu_edit_distance_many_byte_values(emu_aligner):
     common = len(set(a) & set(b))
     if common <= 30:
         assert remap_filter.distance(a, b, library=emu_aligner._libobj) == levenshtein(a, b)
+    # a pair that shares more than 28 distinct symbols is outside what the kernel's class table holds: a clear error
     wide = bytes(range(1, 80))
-    with pytest.raises(_ffi.GotohError):
+    with pytest.raises(ValueError):
         remap_filter.distance(wide, wide, library=emu_aligner._libobj)
 
 
@@ -116,3 +117,19 @@ def test_gpu_remap_filter_incl_hcv_genomes(gpu_aligner):
 @pytest.mark.gpu
 def test_gpu_coordinate_map_incl_hcv(gpu_aligner):
     assert _check_coordinate_map(gpu_aligner._libobj, 10 ** 9) >= 20
+
+
+def test_emu_distance_is_a_drop_in_for_arbitrary_text(emu_aligner):
+    """Levenshtein.distance works on characters and on any alphabet; the device kernel takes at most 30 byte
+    classes per batch.  Non-ASCII text and batches that mix alphabets are re-coded pair by pair."""
+    import string
+    from oracle.oracle2 import levenshtein
+    from gotoh_b200 import remap_filter
+    lib = emu_aligner._libobj
+    assert remap_filter.distance("héllo", "hello", library=lib) == 1
+    wide = string.ascii_letters[:40]               # 40 distinct symbols in the batch, 26 shared by this pair
+    pairs = [(wide, wide[:26][::-1] + "0123456789"), ("ACGTN-ACGT", "ACGTTACGN"), ("abcdefghijklmnopqrstuvwxyz", "abcdefghijklmnopqrstuvwxy"),
+             ("", "abc"), ("αβγδ", "αγδε"), (b"ACGT", b"AGT")]
+    got = remap_filter.distance_batch(pairs, library=lib)
+    exp = [levenshtein(a if isinstance(a, str) else a.decode(), b if isinstance(b, str) else b.decode()) for a, b in pairs]
+    assert got == exp, (got, exp)
