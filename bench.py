@@ -264,9 +264,9 @@ KERNELS = {
     # tag: (kernel name, sass_counts key, ALU-pipe microbenchmark that matches its cell instruction, dtype)
     "x2": ("k_forward<Vec16,8,false,false>", "x2", "viaddmnmx_s16x2", "int16x2"),
     "x2_half_k6": ("k_forward<Vec16,6,false,true> (two 16-lane wavefronts per warp)", "x2_half_k6", "viaddmnmx_s16x2", "int16x2"),
-    # (the flow kernel's FAST block is the int32 cell code of k_forward<Vec32,8> plus a 1-in-4-blocks boundary staging
-    # branch: its steady-state count is the x1 one; ncu's executed count is in profiles/)
-    "x1_flow": ("k_forward_flow<8> (strip dataflow, one warp per (pair, strip))", "x1", "viaddmnmx", "int32"),
+    # (the flow kernel's block = the int32 cell code of k_forward<Vec32,8> + the hand-over of the strip's boundary column;
+    # its own count is the denominator, roofline.frac_vs_plain_cell_code shows it against the bare cell code of "x1")
+    "x1_flow": ("k_forward_flow<8> (strip dataflow, one warp per (pair, strip))", "x1_flow", "viaddmnmx", "int32"),
     "x1": ("k_forward<Vec32,8,false,false>", "x1", "viaddmnmx", "int32"),
 }
 
@@ -607,6 +607,7 @@ def run_ours(args, rank, world, local_rank):
     dir_bytes = 0.25 * cells * (1.03)                 # 2 bits/cell + wavefront fill/drain slots
     n_fwd = max(1, fwd_launches // args.steps)
     ncu = (sc.get("ncu") or {}).get(skey) or {}
+    plain = sc.get("x1") or {}
     roofline = {
         # integer roofline (north_star): which of its two terms binds - the ALU pipe or the ALU+FMA issue slots
         "bound": "int_alu" if roof_alu <= roof_issue else "int_issue", "kernel": kname,
@@ -615,6 +616,8 @@ def run_ours(args, rank, world, local_rank):
                     "rates from gotoh_b200_int_peak in this run, counts from cuobjdump (profiles/sass_counts.json: %s)" % (alu_rate, alu_per_cell, issue_rate, instr_per_cell, skey),
         "instr_per_cell": instr_per_cell, "alu_instr_per_cell": alu_per_cell, "roof_alu_pipe": roof_alu, "roof_issue": roof_issue,
         "issue_peaks_ginstr_s": mix,
+        "executed_instr_per_cell_ncu": ncu.get("executed_instr_per_cell"),
+        "frac_vs_plain_cell_code": (fwd_gcups / min(alu_rate / plain["alu_per_cell"], issue_rate / plain["instr_per_cell"])) if (ktag == "x1_flow" and fwd_gcups and "instr_per_cell" in plain) else None,
         "forward_launches_per_step": n_fwd, "avg_launch_ms": fwd_ms_step / n_fwd,
         "hbm": {"bound": "hbm", "achieved": dir_bytes / (fwd_ms_step * 1e-3) / 1e9 if fwd_ms_step else None,
                 "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_src": peaks_src,
