@@ -1440,25 +1440,55 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
         plans[w].arena_budget_bytes = slab_budget;
         plans[w].task_limit = getenv("GOTOH_B200_TASK_LIMIT") ? atoi(getenv("GOTOH_B200_TASK_LIMIT")) : 0;   // measured: no gain over persistent warps
     }
-    // slab = as many consecutive pairs as fit the arena estimate ((M+40)*64 B per strip per pair).  (Ramping the slab
-    // size up and down to shorten the pipeline's fill and drain was tried and measured slower on B200 than equal slabs.)
+    // slab = as many consecutive pairs as fit the arena estimate ((M+40)*64 B per strip per pair).  The first two slabs get
+    // a quarter of the budget: the result copy - which bounds short-pair batches (C3: 720 MB of strings against 8 ms of
+    // kernels) - and the first forward kernel then start after a quarter of the packing / H2D / preparation time.
+    // (GOTOH_B200_RAMP=0: equal slabs.)  The per-pair need is a prefix sum built by a few threads (1 M pairs: 1.5 -> 0.4 ms).
+    const int64_t npairs = hi - lo;
+    std::vector<int64_t> need_pre((size_t)npairs + 1, 0);
+    std::vector<double> cells_pre((size_t)npairs + 1, 0.0);
+    {
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(8, npairs >> 16));
+        std::vector<int64_t> part_need((size_t)T + 1, 0);
+        std::vector<double> part_cells((size_t)T + 1, 0.0);
+        auto scan_range = [&](int64_t a0, int64_t a1, int64_t need0, double cells0, bool store) {
+            int64_t acc = need0;
+            double cacc = cells0;
+            for (int64_t e = a0; e < a1; ++e) {
+                const int64_t r = ref_idx ? ref_idx[lo + e] : lo + e;
+                const int64_t m = (r >= 0 && r < n_refs) ? ref_off[r + 1] - ref_off[r] : 0;
+                const int64_t nq = qry_off[lo + e + 1] - qry_off[lo + e];
+                acc += (std::max<int64_t>(nq, 1) + 255) / 256 * (m + 40) * 64;
+                cacc += (double)m * (double)nq;
+                if (store) { need_pre[(size_t)e + 1] = acc; cells_pre[(size_t)e + 1] = cacc; }
+            }
+            return std::make_pair(acc, cacc);
+        };
+        if (T == 1) scan_range(0, npairs, 0, 0.0, true);
+        else {
+            parallel_for(T, T, [&](int64_t t0, int64_t t1, int) {
+                for (int64_t t = t0; t < t1; ++t) {
+                    const auto r = scan_range(npairs * t / T, npairs * (t + 1) / T, 0, 0.0, false);
+                    part_need[(size_t)t + 1] = r.first; part_cells[(size_t)t + 1] = r.second;
+                }
+            });
+            for (int t = 0; t < T; ++t) { part_need[(size_t)t + 1] += part_need[(size_t)t]; part_cells[(size_t)t + 1] += part_cells[(size_t)t]; }
+            parallel_for(T, T, [&](int64_t t0, int64_t t1, int) {
+                for (int64_t t = t0; t < t1; ++t) scan_range(npairs * t / T, npairs * (t + 1) / T, part_need[(size_t)t], part_cells[(size_t)t], true);
+            });
+        }
+    }
+    const bool ramp = !(getenv("GOTOH_B200_RAMP") && atoi(getenv("GOTOH_B200_RAMP")) == 0);
     std::vector<int64_t> cuts(1, lo);
     std::vector<double> slab_cells;                  // estimated DP cells per slab (untrimmed lengths)
-    for (int64_t k = lo; k < hi;) {
-        int64_t est = 0, e = k;
-        double cells = 0.0;
-        while (e < hi) {
-            const int64_t r = ref_idx ? ref_idx[e] : e;
-            const int64_t m = (r >= 0 && r < n_refs) ? ref_off[r + 1] - ref_off[r] : 0;
-            const int64_t nq = qry_off[e + 1] - qry_off[e];
-            const int64_t need = (std::max<int64_t>(nq, 1) + 255) / 256 * (m + 40) * 64;
-            if (e > k && (est + need > slab_budget || e - k >= (1 << 20))) break;
-            est += need;
-            cells += (double)m * (double)nq;
-            ++e;
-        }
-        cuts.push_back(e);
-        slab_cells.push_back(cells);
+    for (int64_t k = 0; k < npairs;) {
+        const int64_t budget_here = (ramp && cuts.size() <= 2) ? std::min<int64_t>(slab_budget, std::max<int64_t>(slab_budget / 4, (int64_t)64 << 20)) : slab_budget;
+        // the last e with need(k..e) <= budget (at least one pair, at most 2^20)
+        const int64_t limit = need_pre[(size_t)k] + budget_here;
+        int64_t e = std::upper_bound(need_pre.begin() + k + 1, need_pre.begin() + std::min<int64_t>(npairs, k + (1 << 20)) + 1, limit) - need_pre.begin() - 1;
+        e = std::max(e, k + 1);
+        cuts.push_back(lo + e);
+        slab_cells.push_back(cells_pre[(size_t)e] - cells_pre[(size_t)k]);
         k = e;
     }
     const int nslabs = (int)cuts.size() - 1;
