@@ -483,6 +483,7 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         # verify what was timed: the buffers the LAST timed call filled, against the resident arm's results, all pairs
         ver_pairs = 0
+        e2e_oracle = 0
         if res_fetch is not None:
             same = (np.array_equal(outs[2], res_fetch[2]) and np.array_equal(outs[3], res_fetch[3]) and
                     np.array_equal(outs[0], res_fetch[0]) and np.array_equal(outs[1], res_fetch[1]))
@@ -490,7 +491,7 @@ def run_ours(args, rank, world, local_rank):
                 raise SystemExit("bench.py: e2e (strings) outputs of the timed run differ from the resident arm's - refusing to report a number")
             ver_pairs = last.n
         elif rank == 0 and args.verify > 0:
-            verify_against_oracle(last, strided_strings(outs, last.out_off), args.verify, "e2e strings")
+            e2e_oracle = verify_against_oracle(last, strided_strings(outs, last.out_off), args.verify, "e2e strings")
         if len(jobs) > 1 and rank == 0 and args.verify > 0:
             # several batches share the output buffers: the last batch's timed outputs were compared above; every other
             # batch is re-run once (untimed) and sampled against the oracle
@@ -502,7 +503,7 @@ def run_ours(args, rank, world, local_rank):
             al.align_packed(b.rb, b.ro, b.ridx, b.qb, b.qo, b.gip, b.gep, b.term, b.matrix, out_off=b.out_off, out=outs, device_mask=mask)
         d2h = int(sum(2 * int(b.out_off[-1]) + 8 * b.n for b in jobs))
         h2d = int(sum(len(b.qb) + len(b.rb) + 2 * 64 * (len(b.refs) + 1) + b.n * 72 for b in jobs))
-        e2e["strings"] = {"s": e2e_s, "h2d": h2d, "d2h": d2h, "verified_pairs_vs_resident": ver_pairs}
+        e2e["strings"] = {"s": e2e_s, "h2d": h2d, "d2h": d2h, "verified_pairs_vs_resident": ver_pairs, "verified_pairs_vs_oracle": e2e_oracle}
         strings_ref = (outs[2].copy(), outs[3].copy())        # lengths and scores of the last batch, for the compact check
         sample_ks = list(range(0, last.n, max(1, last.n // 200)))
         strings_sample = {k: strided_strings(outs, last.out_off)(k) for k in sample_ks}
@@ -666,6 +667,7 @@ def run_ours(args, rank, world, local_rank):
                    "arena_chunks_per_step": chunks // args.steps if len(jobs) == 1 else chunks // args.steps, "pairs_int16x2": path_x2 // (args.steps if len(jobs) > 1 else 1),
                    "pairs_int32": path_x1 // (args.steps if len(jobs) > 1 else 1)},
         "bit_exact_verified_pairs": {"resident_vs_oracle": verified, "e2e_strings_vs_resident": e2e.get("strings", {}).get("verified_pairs_vs_resident", 0),
+                                     "e2e_strings_vs_oracle": e2e.get("strings", {}).get("verified_pairs_vs_oracle", 0),
                                      "e2e_compact_vs_strings": e2e.get("compact", {}).get("scores_lengths_verified_pairs", 0)},
         "clocks": clocks,
         "e2e": e2e_line,

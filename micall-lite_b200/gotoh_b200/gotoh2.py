@@ -61,9 +61,10 @@ class Aligner:
         assert len(seq2) > 0, "seq2 cannot be an empty string"
         return self.align_batch([(seq1, seq2)])[0]
 
-    def align_batch(self, pairs):
+    def align_batch(self, pairs, lazy=False):
         """[(seq1, seq2), ...] -> [(aligned1, aligned2, score), ...]; raises RuntimeError like
-        _gotoh2.c:601-603 when a traceback fails."""
+        _gotoh2.c:601-603 when a traceback fails.  ``lazy=True`` returns a sequence that builds each tuple when it is
+        asked for (hundreds of thousands of result tuples cost more Python time than the GPU spends aligning)."""
         pairs = list(pairs)
         if not pairs:
             return []
@@ -92,6 +93,26 @@ class Aligner:
         if rc == _ffi.ETRACEBACK:
             raise RuntimeError("Traceback failed, try local alignment")
         self._libobj.check(rc)
+        if lazy:
+            return LazyAlignments(packing.PackedStrings(out1, out_off, out_len), packing.PackedStrings(out2, out_off, out_len), out_score)
         a = packing.unpack(out1, out_off, out_len)
         b = packing.unpack(out2, out_off, out_len)
         return [(a[k], b[k], int(out_score[k])) for k in range(n)]
+
+
+class LazyAlignments:
+    """Sequence of (aligned1, aligned2, score) over the packed result arrays."""
+
+    def __init__(self, a, b, score):
+        self._a, self._b, self.scores = a, b, score
+
+    def __len__(self):
+        return len(self.scores)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        return self._a[k], self._b[k], int(self.scores[k])
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))

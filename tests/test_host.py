@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol(product_library):
     assert declared == set(_ffi.SYMBOLS), declared ^ set(_ffi.SYMBOLS)
     for sym in declared:
         assert hasattr(product_library.lib, sym), sym
-    assert product_library.version() == 100
+    assert product_library.version() == 200
 
 
 def test_product_tables_match_reference_dump(product_library):

@@ -63,7 +63,12 @@ def run(name, pairs, gop, gep, glob, model, steps, verify, cpu_seconds):
     best = None
     e2e = []
     out = None
+    lazy = []
     for it in range(steps + 1):
+        t0 = time.perf_counter()
+        lz = al.align_batch(pairs, lazy=True)
+        lazy.append(time.perf_counter() - t0)
+        assert lz[0] == lz[0] and len(lz) == len(pairs)
         t0 = time.perf_counter()
         out = al.align_batch(pairs)
         dt = time.perf_counter() - t0
@@ -106,7 +111,7 @@ def run(name, pairs, gop, gep, glob, model, steps, verify, cpu_seconds):
             "ms_reverse": best[3], "ms_walk_emit": best[4], "gcups_forward": cells / (best[2] * 1e-3) / 1e9,
             "gcups_reverse": cells / (best[3] * 1e-3) / 1e9, "gpu_launches": best[5], "arena_bytes": best[6],
             "chunks": best[7], "forward_tasks_int16x2": best[10], "e2e_gcups_c_abi": cells / min(cabi) / 1e9, "e2e_s_c_abi": min(cabi),
-            "h2d_bytes": best[8], "d2h_bytes": best[9], "e2e_gcups_python_api": cells / min(e2e) / 1e9, "verified": len(idx), "mismatches": bad,
+            "h2d_bytes": best[8], "d2h_bytes": best[9], "e2e_gcups_python_api": cells / min(e2e) / 1e9, "e2e_gcups_python_api_lazy": cells / min(lazy[1:]) / 1e9, "verified": len(idx), "mismatches": bad,
             "params": {"gop": gop, "gep": gep, "is_global": glob, "model": model}}
     if cpu_seconds > 0:
         line["cpu_baseline"] = cpu_baseline(pairs, gop, gep, glob, model, cpu_seconds)
