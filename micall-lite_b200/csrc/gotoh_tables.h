@@ -7,7 +7,7 @@
 // The reference refills a process-global int[127][127] on every call; the values never
 // change, so here each table is built once on the host as a list of override rules applied
 // in the reference's order (later rules win), then uploaded per plan as a compact
-// [class][128] slice.  tests/test_tables.py diffs all 3 x 127 x 127 entries against the
+// [class][128] slice.  tests/test_host.py diffs all 3 x 127 x 127 entries against the
 // table dumped from the compiled reference (tests/golden/pairscore_tables.json).
 #pragma once
 #include <stdint.h>

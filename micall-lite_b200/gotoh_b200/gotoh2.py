@@ -69,15 +69,17 @@ class Aligner:
         if not pairs:
             return []
         # identical first sequences (one reference against many reads) are packed once and shared through s1_idx
-        uniq, s1_idx = {}, np.zeros(len(pairs), np.int32)
-        for k, (a, _) in enumerate(pairs):
-            s1_idx[k] = uniq.setdefault(a, len(uniq))
+        uniq = {}
+        s1_idx = np.fromiter((uniq.setdefault(p[0], len(uniq)) for p in pairs), np.int32, count=len(pairs))
         # the library cleans the bytes itself (ASCII upper-case, non-alphabet -> '?', gotoh2.py:70-72); only non-ASCII text
         # goes through the reference's regular expression here, because it works on characters, not on UTF-8 bytes
         s1 = [a if a.isascii() else self.clean_sequence(a) for a in uniq]
-        s2 = [b if b.isascii() else self.clean_sequence(b) for _, b in pairs]
+        s2 = [p[1] for p in pairs]
+        try:
+            b2, o2 = packing.pack(s2, "seq2", ascii_only=True)
+        except UnicodeError:
+            b2, o2 = packing.pack([b if b.isascii() else self.clean_sequence(b) for b in s2], "seq2")
         b1, o1 = packing.pack(s1, "seq1")
-        b2, o2 = packing.pack(s2, "seq2")
         n = len(pairs)
         out_off = packing.out_offsets(o1, s1_idx, o2)
         out1 = np.zeros(int(out_off[-1]), np.uint8)

@@ -16,8 +16,9 @@ def to_bytes(s, what="sequence"):
     return b
 
 
-def pack(seqs, what="sequence"):
-    """list of str/bytes -> (uint8 array, int64 offsets of len n+1)."""
+def pack(seqs, what="sequence", ascii_only=False):
+    """list of str/bytes -> (uint8 array, int64 offsets of len n+1).  ``ascii_only``: raise UnicodeError instead of
+    encoding non-ASCII text as UTF-8 (callers that treat such text differently)."""
     seqs = list(seqs)
     n = len(seqs)
     off = np.zeros(n + 1, dtype=np.int64)
@@ -32,6 +33,10 @@ def pack(seqs, what="sequence"):
                 raise ValueError("embedded null character")
             np.cumsum(np.fromiter(map(len, seqs), dtype=np.int64, count=n), out=off[1:])
             return np.frombuffer(joined.encode("ascii"), dtype=np.uint8), off
+        if ascii_only:
+            raise UnicodeError("non-ASCII text")
+    elif ascii_only and any(isinstance(s, str) and not s.isascii() for s in seqs):
+        raise UnicodeError("non-ASCII text")
     bs = [to_bytes(s, what) for s in seqs]
     np.cumsum([len(b) for b in bs], out=off[1:])
     data = np.frombuffer(b"".join(bs), dtype=np.uint8) if bs else np.zeros(0, dtype=np.uint8)
