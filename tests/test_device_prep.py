@@ -117,3 +117,39 @@ def test_gpu_device_builder_matches_host_builder(gpu_aligner, oracle_port, monke
     _both_builders(gpu_aligner, oracle_port, monkeypatch, 1, arefs, aq, [k % 3 for k in range(len(aq))], 40, 10, 1, n_oracle=3000)
     ref, reads = workloads.c2_reads(30000, seed=16)
     _both_builders(gpu_aligner, oracle_port, monkeypatch, 0, [ref], reads, [0] * len(reads), 10, 3, 1, n_oracle=300)
+    # the most references the device builder takes (64), every query width, several slabs
+    refs, qs, ridx = _ragged(17, 120000, nrefs=64)
+    _both_builders(gpu_aligner, oracle_port, monkeypatch, 0, refs, qs, ridx, 10, 3, 1, n_oracle=800)
+
+
+@pytest.mark.gpu
+def test_gpu_concurrent_callers_share_a_device(gpu_aligner, oracle_port):
+    """Two host threads call the one-shot entry points at the same time (ctypes releases the GIL; the per-device context
+    serialises them): both get their own results."""
+    import threading
+    jobs = []
+    for seed, form in ((21, "strings"), (22, "compact"), (23, "tight")):
+        refs, qs, ridx = _ragged(seed, 20000, nrefs=3)
+        jobs.append((form, refs, qs, ridx))
+    got = {}
+
+    def run(form, refs, qs, ridx):
+        rb, ro = packing.pack(refs)
+        qb, qo = packing.pack(qs)
+        r = np.asarray(ridx, np.int32)
+        fn = {"strings": gpu_aligner.align_packed, "compact": gpu_aligner.align_packed_compact, "tight": gpu_aligner.align_packed_tight}[form]
+        got[form] = fn(rb, ro, r, qb, qo, 10, 3, 1, 0)
+    th = [threading.Thread(target=run, args=j) for j in jobs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for form, refs, qs, ridx in jobs:
+        g = got[form]
+        for k in range(0, len(qs), 97):
+            exp = oracle_port.align_it(refs[ridx[k]], qs[k], 10, 3, 1)
+            if form == "compact":
+                assert g[k] == exp
+            else:
+                o, ln = int(g[2][k]), int(g[3][k])
+                assert (g[0][o:o + ln].tobytes().decode(), g[1][o:o + ln].tobytes().decode(), int(g[4][k])) == exp
