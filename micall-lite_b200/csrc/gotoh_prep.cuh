@@ -151,23 +151,59 @@ __device__ __forceinline__ int prep_bin(const PrepParams& p, int KH, int rank, i
     return (prep_kh_rank(KH) * p.n_used + rank) * PREP_NSLOT + (PREP_NSLOT - N);      // N descending inside the group
 }
 
+// Warp-aggregated counter increment: the lanes of a warp that hit the same counter elect a leader, which adds their
+// number once; every lane gets its own rank.  (One atomic per thread on a handful of hot bins - a batch has a few
+// references and query lengths - serialised 300 k threads: k_prep_bins took 570 us, a quarter of the C3 forward kernel.)
+__device__ __forceinline__ unsigned prep_count_in(uint32_t* counters, int bin, bool active) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xffffffffu, active ? bin : -1);
+    unsigned base = 0;
+    const int leader = __ffs(peers) - 1;
+    if (active && (int)lane == leader) base = atomicAdd(&counters[bin], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 // ---- thread per pair: frame-shift need, worst pair per K, histogram ------------------------------------------------------
 __global__ void __launch_bounds__(256) k_prep_bins(const PrepParams p) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= p.n) return;
-    const int N = p.pairN[k];
-    if (N < 1) return;                                                  // already flagged
-    const int r = p.ref_idx[k];
-    const int M = p.ref_M[r];
-    const int minT = p.scal[16];
-    const long long need = plan_int16_low_need(M, N, p.gip, p.gep, minT);
-    if (need > 32000) { prep_fallback(p, 7); return; }
-    atomicMax(&p.scal[1], (int)need);
-    const int K = plan_pick_K(N);
-    atomicMax(&p.scal[2 + K], (M < N ? M : N) + 1);                     // + 1: the scratch block starts zeroed, 0 = no pair with this K
-    atomicAdd(&p.hist[prep_bin(p, plan_pick_KH(N, p.half_off != 0), p.ref_rank[r], N)], 1u);
-    atomicAdd(&p.acc[0], (unsigned long long)M * (unsigned long long)N);
-    atomicAdd(&p.acc[1], (unsigned long long)(M + N));
+    const int lane = threadIdx.x & 31;
+    const int N = k < p.n ? p.pairN[k] : 0;
+    bool active = N >= 1;                                               // (inactive: beyond n, or already flagged)
+    int r = 0, M = 0, K = 0, bin = 0;
+    long long need = 0;
+    if (active) {
+        r = p.ref_idx[k];
+        M = p.ref_M[r];
+        need = plan_int16_low_need(M, N, p.gip, p.gep, p.scal[16]);
+        if (need > 32000) { prep_fallback(p, 7); active = false; }
+    }
+    if (active) {
+        K = plan_pick_K(N);
+        bin = prep_bin(p, plan_pick_KH(N, p.half_off != 0), p.ref_rank[r], N);
+    }
+    (void)prep_count_in(p.hist, bin, active);
+    // per-warp reductions, one atomic per warp and quantity
+    int v_need = active ? (int)need : 0;
+    unsigned long long cells = active ? (unsigned long long)M * (unsigned long long)N : 0ull, mn_sum = active ? (unsigned long long)(M + N) : 0ull;
+    int worst[5];
+    const int KS[5] = {2, 3, 4, 6, 8};
+#pragma unroll
+    for (int x = 0; x < 5; ++x) worst[x] = (active && K == KS[x]) ? (M < N ? M : N) + 1 : 0;    // + 1: the scratch block starts zeroed, 0 = no pair with this K
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        v_need = max(v_need, __shfl_xor_sync(0xffffffffu, v_need, off));
+        cells += __shfl_xor_sync(0xffffffffu, cells, off);
+        mn_sum += __shfl_xor_sync(0xffffffffu, mn_sum, off);
+#pragma unroll
+        for (int x = 0; x < 5; ++x) worst[x] = max(worst[x], __shfl_xor_sync(0xffffffffu, worst[x], off));
+    }
+    if (lane == 0) {
+        if (v_need) atomicMax(&p.scal[1], v_need);
+#pragma unroll
+        for (int x = 0; x < 5; ++x) if (worst[x]) atomicMax(&p.scal[2 + KS[x]], worst[x]);
+        if (cells) { atomicAdd(&p.acc[0], cells); atomicAdd(&p.acc[1], mn_sum); }
+    }
 }
 
 // ---- one CTA: z4, R, admission, prefix sums over the bins, groups, launches ----------------------------------------------
@@ -266,13 +302,14 @@ __global__ void __launch_bounds__(256) k_prep_layout(const PrepParams p) {
 // ---- thread per pair: PairInfo and task entries ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_prep_scatter(const PrepParams p) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= p.n) return;
-    const int N = p.pairN[k];
-    const int r = p.ref_idx[k];
-    const int M = p.ref_M[r], rank = p.ref_rank[r];
+    const bool active = k < p.n;                                          // (every lane takes part in the warp-wide count)
+    const int N = active ? p.pairN[k] : 1;
+    const int r = active ? p.ref_idx[k] : 0;
+    const int M = active ? p.ref_M[r] : 1, rank = active ? p.ref_rank[r] : 0;
     const int KH = plan_pick_KH(N, p.half_off != 0), K = KH & 15, hw = KH >> 4;
-    const int b = prep_bin(p, KH, rank, N);
-    const unsigned rk = atomicAdd(&p.cursor[b], 1u);
+    const int b = active ? prep_bin(p, KH, rank, N) : 0;
+    const unsigned rk = prep_count_in(p.cursor, b, active);
+    if (!active) return;
     const int g = b / PREP_NSLOT;
     const long long pos = p.bin_pair[b] + rk;                              // plan-order index of this pair
     const long long q = pos - p.bin_pair[g * PREP_NSLOT];                  // index inside the group

@@ -156,6 +156,12 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     for (int l = 0; l < 32; ++l) r |= (unsigned)(simt::slot_as<int>(s, l) & 1) << l;
     return r;
 }
+static inline unsigned __match_any_sync(unsigned, int v) {
+    const uint64_t* s = simt::warp_publish<int>(v);
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l) r |= (unsigned)(simt::slot_as<int>(s, l) == v) << l;
+    return r;
+}
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 
