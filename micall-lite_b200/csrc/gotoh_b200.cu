@@ -1443,52 +1443,49 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     // slab = as many consecutive pairs as fit the arena estimate ((M+40)*64 B per strip per pair).  The first two slabs get
     // a quarter of the budget: the result copy - which bounds short-pair batches (C3: 720 MB of strings against 8 ms of
     // kernels) - and the first forward kernel then start after a quarter of the packing / H2D / preparation time.
-    // (GOTOH_B200_RAMP=0: equal slabs.)  The per-pair need is a prefix sum built by a few threads (1 M pairs: 1.5 -> 0.4 ms).
+    // (GOTOH_B200_RAMP=0: equal slabs.)  The per-pair need is summed per block of 4096 pairs by a few threads; the cuts walk
+    // the block sums and scan pairs only inside the block a cut falls into (1 M pairs: 1.5 -> 0.3 ms; a full per-pair
+    // prefix array cost more in page faults than the serial loop it replaced).
     const int64_t npairs = hi - lo;
-    std::vector<int64_t> need_pre((size_t)npairs + 1, 0);
-    std::vector<double> cells_pre((size_t)npairs + 1, 0.0);
-    {
-        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(8, npairs >> 16));
-        std::vector<int64_t> part_need((size_t)T + 1, 0);
-        std::vector<double> part_cells((size_t)T + 1, 0.0);
-        auto scan_range = [&](int64_t a0, int64_t a1, int64_t need0, double cells0, bool store) {
-            int64_t acc = need0;
-            double cacc = cells0;
-            for (int64_t e = a0; e < a1; ++e) {
-                const int64_t r = ref_idx ? ref_idx[lo + e] : lo + e;
-                const int64_t m = (r >= 0 && r < n_refs) ? ref_off[r + 1] - ref_off[r] : 0;
-                const int64_t nq = qry_off[lo + e + 1] - qry_off[lo + e];
-                acc += (std::max<int64_t>(nq, 1) + 255) / 256 * (m + 40) * 64;
-                cacc += (double)m * (double)nq;
-                if (store) { need_pre[(size_t)e + 1] = acc; cells_pre[(size_t)e + 1] = cacc; }
-            }
-            return std::make_pair(acc, cacc);
-        };
-        if (T == 1) scan_range(0, npairs, 0, 0.0, true);
-        else {
-            parallel_for(T, T, [&](int64_t t0, int64_t t1, int) {
-                for (int64_t t = t0; t < t1; ++t) {
-                    const auto r = scan_range(npairs * t / T, npairs * (t + 1) / T, 0, 0.0, false);
-                    part_need[(size_t)t + 1] = r.first; part_cells[(size_t)t + 1] = r.second;
-                }
-            });
-            for (int t = 0; t < T; ++t) { part_need[(size_t)t + 1] += part_need[(size_t)t]; part_cells[(size_t)t + 1] += part_cells[(size_t)t]; }
-            parallel_for(T, T, [&](int64_t t0, int64_t t1, int) {
-                for (int64_t t = t0; t < t1; ++t) scan_range(npairs * t / T, npairs * (t + 1) / T, part_need[(size_t)t], part_cells[(size_t)t], true);
-            });
+    auto pair_need = [&](int64_t e, double* cells) -> int64_t {
+        const int64_t r = ref_idx ? ref_idx[lo + e] : lo + e;
+        const int64_t m = (r >= 0 && r < n_refs) ? ref_off[r + 1] - ref_off[r] : 0;
+        const int64_t nq = qry_off[lo + e + 1] - qry_off[lo + e];
+        *cells += (double)m * (double)nq;
+        return (std::max<int64_t>(nq, 1) + 255) / 256 * (m + 40) * 64;
+    };
+    enum { CUT_BLOCK = 4096 };
+    const int64_t nblocks = (npairs + CUT_BLOCK - 1) / CUT_BLOCK;
+    std::vector<int64_t> blk_need((size_t)nblocks);
+    std::vector<double> blk_cells((size_t)nblocks);
+    parallel_for(nblocks, (int)std::max<int64_t>(1, std::min<int64_t>(8, nblocks / 16)), [&](int64_t b0, int64_t b1, int) {
+        for (int64_t bk = b0; bk < b1; ++bk) {
+            int64_t acc = 0;
+            double c = 0.0;
+            for (int64_t e = bk * CUT_BLOCK; e < std::min<int64_t>(npairs, (bk + 1) * CUT_BLOCK); ++e) acc += pair_need(e, &c);
+            blk_need[(size_t)bk] = acc; blk_cells[(size_t)bk] = c;
         }
-    }
+    });
     const bool ramp = !(getenv("GOTOH_B200_RAMP") && atoi(getenv("GOTOH_B200_RAMP")) == 0);
     std::vector<int64_t> cuts(1, lo);
     std::vector<double> slab_cells;                  // estimated DP cells per slab (untrimmed lengths)
     for (int64_t k = 0; k < npairs;) {
         const int64_t budget_here = (ramp && cuts.size() <= 2) ? std::min<int64_t>(slab_budget, std::max<int64_t>(slab_budget / 4, (int64_t)64 << 20)) : slab_budget;
-        // the last e with need(k..e) <= budget (at least one pair, at most 2^20)
-        const int64_t limit = need_pre[(size_t)k] + budget_here;
-        int64_t e = std::upper_bound(need_pre.begin() + k + 1, need_pre.begin() + std::min<int64_t>(npairs, k + (1 << 20)) + 1, limit) - need_pre.begin() - 1;
-        e = std::max(e, k + 1);
+        int64_t est = 0, e = k;
+        double cells = 0.0;
+        while (e < npairs && e - k < (1 << 20)) {
+            if (e % CUT_BLOCK == 0 && e + CUT_BLOCK <= npairs && e - k + CUT_BLOCK <= (1 << 20) && est + blk_need[(size_t)(e / CUT_BLOCK)] <= budget_here) {
+                est += blk_need[(size_t)(e / CUT_BLOCK)]; cells += blk_cells[(size_t)(e / CUT_BLOCK)]; e += CUT_BLOCK;   // a whole block fits
+                continue;
+            }
+            double c1 = 0.0;
+            const int64_t need = pair_need(e, &c1);
+            if (e > k && est + need > budget_here) break;
+            est += need; cells += c1;
+            ++e;
+        }
         cuts.push_back(lo + e);
-        slab_cells.push_back(cells_pre[(size_t)e] - cells_pre[(size_t)k]);
+        slab_cells.push_back(cells);
         k = e;
     }
     const int nslabs = (int)cuts.size() - 1;
