@@ -1123,7 +1123,6 @@ int plan_build_device(gotoh_b200_plan* pl, const uint8_t* ref_bytes, const int64
     }
     if (sum.arena_u4 * 16 > budget) return GOTOH_B200_OK;
     // ---- device buffers of the plan -----------------------------------------------------------------------------------------
-    pl->out_mode = pl->out_mode;
     if (out_off) { pl->out_base = out_off[pair_begin]; pl->out_bytes = out_off[pair_end] - out_off[pair_begin]; }
     else { pl->out_base = 0; pl->out_bytes = sum.sum_mn; }
     CU(ws->d_pairs.ensure((size_t)n));
@@ -1522,7 +1521,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
     };
     auto is_failed = [&]() { std::lock_guard<std::mutex> g(order_mu); return failed; };
     const bool inject_fetch_failure = getenv("GOTOH_B200_TEST_FAIL_FETCH") != nullptr;    // tests: a D2H enqueue that fails
-    auto builder = [&](int b) {
+    auto builder_body = [&](int b) {
         if (cudaSetDevice(dev) != cudaSuccess) { fail_and_wake(b, fail(GOTOH_B200_ECUDA, "cudaSetDevice failed")); return; }
         int mine = 0;
         for (int slab = b; slab < nslabs && !is_failed(); slab += builders, ++mine) {
@@ -1609,6 +1608,16 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
                 state[(size_t)slab] = 1;
                 order_cv.notify_all();
             }
+        }
+    };
+    // a builder thread must not die on an exception (std::terminate) nor leave the others waiting
+    auto builder = [&](int b) {
+        try {
+            builder_body(b);
+        } catch (const std::bad_alloc&) {
+            fail_and_wake(b, fail(GOTOH_B200_ENOMEM, "out of host memory in a builder thread"));
+        } catch (const std::exception& e) {
+            fail_and_wake(b, fail(GOTOH_B200_ECUDA, "internal error in a builder thread: %s", e.what()));
         }
     };
     // The collector (tight / compact forms; the calling thread): in slab order, waits for a slab's phase A, learns its
@@ -1822,6 +1831,18 @@ int align_batch_impl(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n
         if (rcs[d]) return fail(rcs[d], "device %d: %s", devs[d], msgs[d].c_str());
     return GOTOH_B200_OK;
 }
+// no C++ exception crosses the C boundary
+int align_batch_guarded(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs, const int32_t* ref_idx,
+                        const uint8_t* qry_bytes, const int64_t* qry_off, int64_t n_pairs, int32_t gip, int32_t gep,
+                        int32_t use_terminal, int32_t matrix_id, const OutSpec& out, int64_t cap, uint32_t device_mask) {
+    try {
+        return align_batch_impl(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, out, cap, device_mask);
+    } catch (const std::bad_alloc&) {
+        return fail(GOTOH_B200_ENOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(GOTOH_B200_ECUDA, "internal error: %s", e.what());
+    }
+}
 }  // namespace
 
 extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
@@ -1835,7 +1856,7 @@ extern "C" int32_t gotoh_b200_align_batch(const uint8_t* ref_bytes, const int64_
     if (!out_ref || !out_qry || !out_len || !out_score) return fail(GOTOH_B200_EINVAL, "NULL output pointer");
     OutSpec o;
     o.mode = OUT_STRIDED; o.out_ref = out_ref; o.out_qry = out_qry; o.out_off_in = out_off; o.out_len = out_len; o.out_score = out_score;
-    return align_batch_impl(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, o, 0, device_mask);
+    return align_batch_guarded(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, o, 0, device_mask);
 }
 
 extern "C" int32_t gotoh_b200_align_batch_tight(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
@@ -1849,7 +1870,7 @@ extern "C" int32_t gotoh_b200_align_batch_tight(const uint8_t* ref_bytes, const 
     if (!out_ref || !out_qry || !out_off || !out_len || !out_score || out_cap < 0) return fail(GOTOH_B200_EINVAL, "NULL output pointer or negative capacity");
     OutSpec o;
     o.mode = OUT_TIGHT; o.out_ref = out_ref; o.out_qry = out_qry; o.out_off = out_off; o.out_len = out_len; o.out_score = out_score;
-    return align_batch_impl(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, o, out_cap, device_mask);
+    return align_batch_guarded(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, o, out_cap, device_mask);
 }
 
 extern "C" int32_t gotoh_b200_align_batch_compact(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n_refs,
@@ -1863,7 +1884,7 @@ extern "C" int32_t gotoh_b200_align_batch_compact(const uint8_t* ref_bytes, cons
     if (!out_rec || !out_ops || !out_ops_off || out_ops_cap < 0) return fail(GOTOH_B200_EINVAL, "NULL output pointer or negative capacity");
     OutSpec o;
     o.mode = OUT_COMPACT; o.out_rec = out_rec; o.out_ops = out_ops; o.out_off = out_ops_off;
-    return align_batch_impl(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, o, out_ops_cap, device_mask);
+    return align_batch_guarded(ref_bytes, ref_off, n_refs, ref_idx, qry_bytes, qry_off, n_pairs, gip, gep, use_terminal, matrix_id, o, out_ops_cap, device_mask);
 }
 
 // Host-ceiling probe: plain device-to-host copies into the caller's (pinned) buffer, CUDA-event timed.
@@ -1875,24 +1896,32 @@ extern "C" int32_t gotoh_b200_d2h_probe(int32_t device, void* host_buf, int64_t 
     // scratch of at most 1 GB, copied repeatedly to successive positions of the host buffer
     const int64_t piece = std::min<int64_t>(bytes, (int64_t)1 << 30);
     void* d = nullptr;
-    CU(cudaMalloc(&d, (size_t)piece));
-    cudaStream_t st;
-    cudaEvent_t e0, e1;
-    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaMemsetAsync(d, 0x2d, (size_t)piece, st));
-    CU(cudaStreamSynchronize(st));
-    CU(cudaEventRecord(e0, st));
-    for (int r = 0; r < reps; ++r)
-        for (int64_t at = 0; at < bytes; at += piece)
-            CU(cudaMemcpyAsync((char*)host_buf + at, d, (size_t)std::min<int64_t>(piece, bytes - at), cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(e1, st));
-    CU(cudaEventSynchronize(e1));
+    cudaStream_t st = 0;
+    cudaEvent_t e0 = 0, e1 = 0;
     float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
+    auto run = [&]() -> int {
+        CU(cudaMalloc(&d, (size_t)piece));
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaMemsetAsync(d, 0x2d, (size_t)piece, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaEventRecord(e0, st));
+        for (int r = 0; r < reps; ++r)
+            for (int64_t at = 0; at < bytes; at += piece)
+                CU(cudaMemcpyAsync((char*)host_buf + at, d, (size_t)std::min<int64_t>(piece, bytes - at), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(e1, st));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        return GOTOH_B200_OK;
+    };
+    const int rc = run();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    if (d) cudaFree(d);
+    if (rc) return rc;
     *seconds = ms * 1e-3;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st); cudaFree(d);
     return GOTOH_B200_OK;
 }
 
