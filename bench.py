@@ -99,6 +99,18 @@ CONFIGS = {
 }
 
 
+def _c5_batch_arrays(job):
+    """Batch b of the C5 mix, this rank's contiguous share: 80 % C2 reads, 20 % C3 windows."""
+    from gotoh_b200 import workloads
+    b, per, rank, world = job
+    n2, n3 = int(per * 0.8), per - int(per * 0.8)
+    lo2, hi2 = workloads.shard_range(n2, rank, world)
+    lo3, hi3 = workloads.shard_range(n3, rank, world)
+    ref, qb, qo = workloads.c2_reads_packed(hi2 - lo2, seed=20260105 + 1000 * b + rank)
+    refs, ridx, qb3, qo3 = workloads.c3_queries_packed(hi3 - lo3, seed=20260205 + 1000 * b + rank)
+    return ref, qb, qo, refs, ridx, qb3, qo3
+
+
 def make_batches(config, pairs, rank, world):
     """The batches THIS rank aligns per step."""
     from gotoh_b200 import packing, workloads
@@ -123,14 +135,16 @@ def make_batches(config, pairs, rank, world):
         # statistics, seeded per (batch, rank)), which keeps set-up time off the GPU box's clock.
         nb = max(1, pairs // 1000000)
         per = pairs // nb
+        jobs = [(b, per, rank, world) for b in range(nb)]
+        if world == 1 and nb > 1:
+            # one process generates the whole job: spread the batches over a few processes (set-up time only)
+            with multiprocessing.get_context("fork").Pool(min(nb, os.cpu_count() or 1)) as pool:
+                parts = pool.map(_c5_batch_arrays, jobs)
+        else:
+            parts = [_c5_batch_arrays(j) for j in jobs]
         out = []
-        for b in range(nb):
-            n2, n3 = int(per * 0.8), per - int(per * 0.8)
-            lo2, hi2 = workloads.shard_range(n2, rank, world)
-            lo3, hi3 = workloads.shard_range(n3, rank, world)
-            ref, qb, qo = workloads.c2_reads_packed(hi2 - lo2, seed=20260105 + 1000 * b + rank)
-            out.append(Batch(NT, 10, 3, 1, [ref], np.zeros(hi2 - lo2, np.int32), qb, qo))
-            refs, ridx, qb3, qo3 = workloads.c3_queries_packed(hi3 - lo3, seed=20260205 + 1000 * b + rank)
+        for (ref, qb, qo, refs, ridx, qb3, qo3) in parts:
+            out.append(Batch(NT, 10, 3, 1, [ref], np.zeros(len(qo) - 1, np.int32), qb, qo))
             out.append(Batch(HIV25, 40, 10, 1, refs, ridx, qb3, qo3))
         return out
     raise SystemExit("unknown config %r" % config)
