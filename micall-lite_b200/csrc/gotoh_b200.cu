@@ -1793,24 +1793,43 @@ int align_batch_impl(const uint8_t* ref_bytes, const int64_t* ref_off, int64_t n
     std::vector<OutSpec> outs((size_t)D, out);
     outs[0].cap_lo = 0; outs[(size_t)D - 1].cap_hi = cap;
     if (D > 1) {
-        // tight / compact forms: each device fills its own slice of the caller's capacity, in proportion to the
-        // worst-case size of its pairs (bytes: M+N; words: ceil((M+N)/16))
-        std::vector<double> pre((size_t)n_pairs + 1, 0.0), wpre((size_t)n_pairs + 1, 0.0);
-        for (int64_t k = 0; k < n_pairs; ++k) {
+        // Contiguous split of equal estimated cell count.  Tight / compact forms: each device fills its own slice of the
+        // caller's capacity, in proportion to the worst-case size of its pairs (bytes: M+N; words: ceil((M+N)/16)).
+        // Both come from per-block sums built by a few threads; a cut scans pairs only inside its block (a per-pair prefix
+        // array cost ~6 ms per call of 1 M pairs in one host process driving 8 GPUs).
+        auto pair_cost = [&](int64_t k, double* w) -> double {
             const int64_t r = ref_idx ? ref_idx[k] : k;
             const double m = (r >= 0 && r < n_refs) ? (double)(ref_off[r + 1] - ref_off[r]) : 1.0;
             const double nq = (double)(qry_off[k + 1] - qry_off[k]);
-            pre[(size_t)k + 1] = pre[(size_t)k] + std::max(1.0, m) * std::max<double>(1.0, nq);
-            wpre[(size_t)k + 1] = wpre[(size_t)k] + (out.mode == OUT_COMPACT ? std::floor((m + nq + 15) / 16) : m + nq);
-        }
+            *w += (out.mode == OUT_COMPACT ? std::floor((m + nq + 15) / 16) : m + nq);
+            return std::max(1.0, m) * std::max<double>(1.0, nq);
+        };
+        enum { SPLIT_BLOCK = 4096 };
+        const int64_t nblocks = (n_pairs + SPLIT_BLOCK - 1) / SPLIT_BLOCK;
+        std::vector<double> blk_c((size_t)nblocks), blk_w((size_t)nblocks);
+        parallel_for(nblocks, (int)std::max<int64_t>(1, std::min<int64_t>(8, nblocks / 16)), [&](int64_t b0, int64_t b1, int) {
+            for (int64_t bk = b0; bk < b1; ++bk) {
+                double c = 0.0, w = 0.0;
+                for (int64_t k = bk * SPLIT_BLOCK; k < std::min<int64_t>(n_pairs, (bk + 1) * SPLIT_BLOCK); ++k) c += pair_cost(k, &w);
+                blk_c[(size_t)bk] = c; blk_w[(size_t)bk] = w;
+            }
+        });
+        double total_c = 0.0, total_w = 0.0;
+        for (int64_t bk = 0; bk < nblocks; ++bk) { total_c += blk_c[(size_t)bk]; total_w += blk_w[(size_t)bk]; }
+        int64_t bk = 0;
+        double acc_c = 0.0, acc_w = 0.0;                       // sums of the blocks before bk
         for (int d = 1; d < D; ++d) {
-            const double target = pre[(size_t)n_pairs] * d / D;
-            cut[d] = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
-            cut[d] = std::max(cut[d], cut[d - 1] + 1);
-            cut[d] = std::min<int64_t>(cut[d], n_pairs - (D - d));
-        }
-        for (int d = 1; d < D; ++d) {
-            const double f = wpre[(size_t)n_pairs] > 0 ? wpre[(size_t)cut[d]] / wpre[(size_t)n_pairs] : 0.0;
+            const double target = total_c * d / D;
+            while (bk < nblocks && acc_c + blk_c[(size_t)bk] < target) { acc_c += blk_c[(size_t)bk]; acc_w += blk_w[(size_t)bk]; ++bk; }
+            int64_t k = std::min(n_pairs, bk * SPLIT_BLOCK);
+            double c = acc_c, w = acc_w;
+            while (k < std::min<int64_t>(n_pairs, (bk + 1) * SPLIT_BLOCK) && c < target) c += pair_cost(k++, &w);
+            // every device gets at least one pair: clamping moves the cut by a few pairs at most, the capacity share follows it
+            const int64_t kc = std::min<int64_t>(std::max(k, cut[d - 1] + 1), n_pairs - (D - d));
+            for (; k < kc; ++k) (void)pair_cost(k, &w);
+            for (; k > kc; --k) { double back = 0.0; (void)pair_cost(k - 1, &back); w -= back; }
+            cut[d] = kc;
+            const double f = total_w > 0 ? w / total_w : 0.0;
             outs[(size_t)d].cap_lo = outs[(size_t)d - 1].cap_hi = (int64_t)std::floor((double)cap * f);
         }
     }

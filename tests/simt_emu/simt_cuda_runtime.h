@@ -22,7 +22,8 @@ struct cudaDeviceProp {
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "simt-emu error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+// SIMT_EMU_DEVICES=n: n emulated devices (they share the host's memory; enough to exercise the multi-device sharding logic)
+static inline cudaError_t cudaGetDeviceCount(int* n) { const char* e = std::getenv("SIMT_EMU_DEVICES"); *n = e ? std::atoi(e) : 1; if (*n < 1) *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }

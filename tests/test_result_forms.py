@@ -127,6 +127,24 @@ def test_emu_failed_result_copy_does_not_hang(emu_aligner, monkeypatch, mode):
     assert isinstance(res["r"], _ffi.GotohError) and "injected" in str(res["r"])
 
 
+def test_emu_multi_device_sharding_all_forms(emu_aligner, oracle_port, monkeypatch):
+    """The library's own static sharding (device_mask, one host thread per device, capacity slices for the tight and
+    compact forms) on three emulated devices: same bytes as one device, for every result form."""
+    monkeypatch.setenv("SIMT_EMU_DEVICES", "3")
+    monkeypatch.setenv("GOTOH_B200_SLAB_MB", "1")
+    assert emu_aligner.device_count() == 3
+    refs, qs = _mixed_batch(17, 150)
+    s, t, c = _check_forms(emu_aligner, oracle_port, 0, refs, qs, 10, 3, 1, n_oracle=30, device_mask=0b111)
+    one = emu_aligner.align_packed(*packing.pack(refs), None, *packing.pack(qs), 10, 3, 1, 0, device_mask=1)
+    assert (one[0] == s[0]).all() and (one[1] == s[1]).all() and (one[3] == s[3]).all() and (one[4] == s[4]).all()
+    assert (np.diff(t[2]) >= s[3][:-1]).all()                     # increasing, gaps only at device boundaries
+    # fewer pairs than devices, and a device index that is not there
+    got = emu_aligner.align_batch(refs[:2], qs[:2], 10, 3, 1, 0, devices=[0, 1, 2], compact=True)
+    assert [got[k] for k in range(2)] == [oracle_port.align_it(refs[k], qs[k], 10, 3, 1) for k in range(2)]
+    with pytest.raises(_ffi.GotohError):
+        emu_aligner.align_batch(refs[:2], qs[:2], 10, 3, 1, 0, devices=[5])
+
+
 def test_emu_device_index_out_of_range_is_rejected(emu_aligner):
     with pytest.raises(ValueError):
         emu_aligner.align_batch(["ACGT"], ["ACG"], 5, 1, 1, 0, devices=[32])
