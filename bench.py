@@ -691,6 +691,8 @@ def run_ours(args, rank, world, local_rank):
                          "sample": "%d pairs of the same workload (first pairs of each batch, same generator/seed) over %d processes, %.1f s" % (sum(b.n for b in sample), cores, cs),
                          "gcups_per_core": cg / cores},
     }
+    if args.emu:
+        line["emu_selftest"] = "kernel sources under the CPU SIMT emulator: a self-test of this script, NOT a measurement"
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
