@@ -68,9 +68,9 @@ def _both_builders(aligner, oracle, monkeypatch, matrix, refs, qs, ridx, gip, ge
 @pytest.mark.parametrize("half", ["1", "0"])
 def test_emu_device_builder_matches_host_builder(emu_aligner, oracle_port, monkeypatch, half):
     monkeypatch.setenv("GOTOH_B200_HALF", half)
-    refs, qs, ridx = _ragged(3, 500)
+    refs, qs, ridx = _ragged(3, 320)
     _both_builders(emu_aligner, oracle_port, monkeypatch, 0, refs, qs, ridx, 10, 3, 1)
-    _both_builders(emu_aligner, oracle_port, monkeypatch, 0, refs, qs, ridx, 10, 10, 0)
+    _both_builders(emu_aligner, oracle_port, monkeypatch, 0, refs, qs[:160], ridx[:160], 10, 10, 0)
     arefs, aq = workloads.c3_queries(301, seed=5)
     _both_builders(emu_aligner, oracle_port, monkeypatch, 1, arefs, aq, [k % 3 for k in range(301)], 40, 10, 1)
 
