@@ -1660,7 +1660,12 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
         }
     };
     if (builders == 1 && !two_phase) builder(0);
-    else {
+    else if (nslabs == 1) {
+        // a small call (one slab): no threads - the builder enqueues, then this thread collects
+        builder(0);
+        if (cudaSetDevice(dev) != cudaSuccess) fail_and_wake(builders, fail(GOTOH_B200_ECUDA, "cudaSetDevice failed"));
+        else collector();
+    } else {
         std::vector<std::thread> th;
         for (int b = 0; b < builders; ++b) th.emplace_back(builder, b);
         if (two_phase) {
