@@ -388,8 +388,21 @@ struct Wave {
 #pragma unroll
                 for (int k = 0; k < K; ++k) { S[k] = V::add(S[k], d); P[k] = V::add(P[k], d); }
                 sdiag = V::add(sdiag, d);
-                if (lane == 0) diag0 = V::add(diag0, d);
                 best = V::add(best, d);
+                if (lane == 0) {
+                    diag0 = V::add(diag0, d);
+                    // Column 0 as the Q recurrence sees it (gotoh.cpp:290-293: s = t_i = u + i*v, q = t_i + u) is
+                    // 4(u - base*g) resp. 4(2u - base*g) + 2 in this frame: it moves with the base like every other stored
+                    // value.  (Round 1 kept the injected constants fixed, which is only right until the first rebase row: with a
+                    // small gip the stale, too high seed could win column 1 against a mismatch right after a rebase row - found
+                    // by tools/fuzz_emu.py, gip = 0 / gep = 10.)  The seeds are floored where the add of the next cell cannot
+                    // leave 16 bits; a candidate that low never wins: every real stored value is >= 0 in the shifted frame.
+                    const int u4 = V::lo(c_sl0) - z4;
+                    const T ns = V::addmax((T)inj_s, d, V::both(-32000 - u4));
+                    const T nq = V::addmax((T)inj_q, d, V::both(-32000));
+                    inj_s = V::raw(ns); inj_q = V::raw(nq);
+                    Sl = ns; Ql = nq;        // this row's injection was made in the old frame, a few lines up
+                }
             }
         }
         Sd_in = Sl;
@@ -642,8 +655,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, GOTOH_MIN_CTAS) k_forward(cons
             w.strip = strip;
             w.j0 = j0;
             w.last_strip = (strip == nstrips - 1);
+            w.set_injection(strip == 0);      // (per task: the int16x2 rebase rows move the injected column-0 seeds)
             if (MULTI) {
-                w.set_injection(strip == 0);
                 w.bnd_in = bnd0 + (int64_t)((strip + 1) & 1) * p.bnd_stride;
                 w.bnd_out = bnd0 + (int64_t)(strip & 1) * p.bnd_stride;
             }

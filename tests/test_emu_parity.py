@@ -238,3 +238,29 @@ def test_emu_wrapper_semantics(emu_aligner, oracle_port):
     assert emu_aligner.align_it("  ACGT\n", "\tACT \r\n", 5, 1, 1) == ("ACGT", "AC-T", 9)
     assert emu_aligner.align_it_aa_rb("K-F-R", "KF--GR", 4, 2) == oracle_port.align_it_aa_rb("K-F-R", "KF--GR", 4, 2)
     assert emu_aligner.align_it_aa("WWWWKFR", "KFR", 40, 10, 0) == ("WWWWKFR", "----KFR", 104)
+
+
+def test_emu_rebase_rows_move_the_column0_seed(emu_aligner, oracle_port, forced_path):
+    """Regression (found by tools/fuzz_emu.py; present since round 1): in the int16x2 frame the column-0 seed of the Q
+    recurrence is 4(u - base*g), so it has to move at every rebase row like all other stored values.  The stale seed only
+    wins with a small gip, right after a rebase row, against a first-column mismatch: gip = 0, gep = 10, and a second pair
+    whose width forces the plan's rebase period down to 32 rows."""
+    refs = ['HNQRXSTW-CLBCRYNXYBXQFYXKRABSQKNEGPPMZTPNPFCEGZLHYNVVXMFK-**-EDPFCWXTZF*R*DXAXQXVPTRWXKYXGNBMQXMDGYBYEVFSCZRMKRZD*XXDKLECMTLCEFNRDKBRFYTYFRMCSADKZQXWVEZXFEA-AAYC', 'MVTZN*HKZS-MHEWVHSEAMSNZ-ZKDMXCLGNMPEEZVZM-WCDMEWMNCNZ*XFFQBFN-RB-WGGSHNIF-NT-XRRPXFXQYHXZQNBYCLQFXLFINBPRLQB-LQ*QCLAZWNVWQWWLABRNCSBLL*YI-TZVTGI-TARXTCTHXKA*GHH*SMEGV*YXWRG-HN-*SHYM*ZSDTXEKEDKHHSDEDT-NLXWKIEMPAMM*RDGZPCEGHSQVGMENLATHWFKVRFS-*-WKQKMCP']
+    qs = ['FKHHSDEDT-NLXWKIEMPAMM*RDGZPCEGHSQVGMENLAKHWFKVRFS-*-WKQKMCP', 'VSTXWXKLKQSM--WFRRWKA*FH*STNGY*XBGHQEFMNTKM**ZKKMFBTAKMPGFXYCGYYBN*WQRN-QBB-FLNYMKQWM-KHKAZGDIDIWTPQBIYKLQCTDBBVGVGHMQNKKAW*TFVZANITTSQNQQTPAXIYZH-DXVHVGTXQSVQXDMZQ-SKNLGKGTXBWSBTYI-KSCGZBLK*QHBAZGVZLKTDSRTDNRZNAWHMSHYFZII*QYLMFWTGLBDZG']
+    ridx = [1, 0]
+    got = emu_aligner.align_batch(refs, qs, 0, 10, 1, 1, ref_idx=ridx)
+    for k in range(len(qs)):
+        assert got[k] == oracle_port.align_it_aa(refs[ridx[k]], qs[k], 0, 10, 1), k
+    # the same rule at scale: random amino-acid pairs, tiny gap-open penalties, one wide pair per batch
+    rng = random.Random(99)
+    alpha = "ARNDCQEGHILKMFPSTWYVBZX*-"
+    for gip, gep in ((0, 10), (1, 7), (0, 3)):
+        refs = ["".join(rng.choice(alpha) for _ in range(rng.randint(100, 260))) for _ in range(3)]
+        qs, ridx = [], []
+        for _ in range(90):
+            r = rng.randrange(3)
+            qs.append("".join(rng.choice(alpha) for _ in range(rng.randint(1, 250))))
+            ridx.append(r)
+        got = emu_aligner.align_batch(refs, qs, gip, gep, 1, 1, ref_idx=ridx)
+        for k in range(len(qs)):
+            assert got[k] == oracle_port.align_it_aa(refs[ridx[k]], qs[k], gip, gep, 1), (gip, gep, k)

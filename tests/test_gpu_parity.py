@@ -267,3 +267,21 @@ def test_gpu_full_size_c2_properties(gpu_aligner, oracle_port):
         s1, s2, ln = int(out_off[k]), int(r_off[m - 1 - k]), int(out_len[k])
         assert (out_b[s1:s1 + ln] == g2[1][s2:s2 + ln]).all()
         assert (out_a[s1:s1 + ln] == g2[0][s2:s2 + ln]).all()
+
+
+def test_gpu_rebase_rows_move_the_column0_seed(gpu_aligner, oracle_port, forced_path):
+    """GPU twin of tests/test_emu_parity.py::test_emu_rebase_rows_move_the_column0_seed, plus a larger random batch with
+    tiny gap-open penalties and a rebase period of 32 rows."""
+    import test_emu_parity
+    test_emu_parity.test_emu_rebase_rows_move_the_column0_seed(gpu_aligner, oracle_port, forced_path)
+    rng = random.Random(199)
+    alpha = "ARNDCQEGHILKMFPSTWYVBZX*-"
+    refs = ["".join(rng.choice(alpha) for _ in range(rng.randint(60, 400))) for _ in range(5)]
+    qs, ridx = [], []
+    for _ in range(6000):
+        qs.append("".join(rng.choice(alpha) for _ in range(rng.randint(1, 256))))
+        ridx.append(rng.randrange(5))
+    for gip, gep in ((0, 10), (1, 4), (0, 1)):
+        got = gpu_aligner.align_batch(refs, qs, gip, gep, 1, 1, ref_idx=ridx)
+        for k in range(len(qs)):
+            assert got[k] == oracle_port.align_it_aa(refs[ridx[k]], qs[k], gip, gep, 1), (gip, gep, k)
