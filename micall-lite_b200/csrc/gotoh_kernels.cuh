@@ -397,9 +397,11 @@ struct Wave {
                     // small gip the stale, too high seed could win column 1 against a mismatch right after a rebase row - found
                     // by tools/fuzz_emu.py, gip = 0 / gep = 10.)  The seeds are floored where the add of the next cell cannot
                     // leave 16 bits; a candidate that low never wins: every real stored value is >= 0 in the shifted frame.
-                    const int u4 = V::lo(c_sl0) - z4;
-                    const T ns = V::addmax((T)inj_s, d, V::both(-32000 - u4));
-                    const T nq = V::addmax((T)inj_q, d, V::both(-32000));
+                    // (32-bit arithmetic per half: a seed that sits at its floor must not wrap when the next delta is added)
+                    const int u4 = V::lo(c_sl0) - z4, dv = -(rebase_mask + 1) * g4;
+                    const int fs = -32000 - u4, fq = -32000;
+                    const T ns = V::pack(max(V::lo((T)inj_s) + dv, fs), max(V::hi((T)inj_s) + dv, fs));
+                    const T nq = V::pack(max(V::lo((T)inj_q) + dv, fq), max(V::hi((T)inj_q) + dv, fq));
                     inj_s = V::raw(ns); inj_q = V::raw(nq);
                     Sl = ns; Ql = nq;        // this row's injection was made in the old frame, a few lines up
                 }
