@@ -264,3 +264,16 @@ def test_emu_rebase_rows_move_the_column0_seed(emu_aligner, oracle_port, forced_
         got = emu_aligner.align_batch(refs, qs, gip, gep, 1, 1, ref_idx=ridx)
         for k in range(len(qs)):
             assert got[k] == oracle_port.align_it_aa(refs[ridx[k]], qs[k], gip, gep, 1), (gip, gep, k)
+
+
+def test_emu_many_rebase_rows_on_the_c2_shape(emu_aligner, oracle_port):
+    """251-nt reads against the 3039-nt pol seed with gep = 10 rebase every 256 rows: the column-0 seeds reach their floor
+    after four rebase rows and must stay there (a 16-bit wrap-around there put 37 of the 123 golden shapes off on the GPU
+    before the floor was computed in 32 bits)."""
+    from gotoh_b200 import workloads
+    ref, reads = workloads.c2_reads(8, seed=5)
+    reads = ["T" + r[1:] for r in reads]
+    for gip, gep, term in ((0, 10, 1), (10, 10, 0), (1, 3, 1)):
+        got = emu_aligner.align_batch([ref], reads, gip, gep, term, 0, ref_idx=[0] * len(reads))
+        for g, r in zip(got, reads):
+            assert g == oracle_port.align_it(ref, r, gip, gep, term), (gip, gep, term)
