@@ -126,7 +126,7 @@ def main():
         try:
             doc[tag] = count(pat, 4, 3 if tag.endswith("k3") else 8, npair, sh, per)
         except Exception as e:      # a kernel without a 128-bit store in its loop (score-only) has no such block
-            doc[tag] = {"error": str(e)}
+            doc[tag] = {"error": "no steady-state block with a 128-bit store found (%s)" % e}
     prev = os.path.join(ROOT, "profiles", "sass_counts.json")
     if os.path.exists(prev):
         try:
