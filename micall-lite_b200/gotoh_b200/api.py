@@ -159,7 +159,7 @@ class Aligner:
                                                                 device_mask=mask)
         a = packing.unpack(o_ref, o_off, o_len)
         b = packing.unpack(o_qry, o_off, o_len)
-        return [(a[k], b[k], int(o_score[k])) for k in range(len(queries))]
+        return list(zip(a, b, o_score.tolist()))
 
     # ---- the reference's three callables ------------------------------------------------
     def _one(self, standard, seq, gip, gep, term, matrix):

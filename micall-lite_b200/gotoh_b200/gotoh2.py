@@ -69,12 +69,14 @@ class Aligner:
         if not pairs:
             return []
         # identical first sequences (one reference against many reads) are packed once and shared through s1_idx
-        uniq = {}
-        s1_idx = np.fromiter((uniq.setdefault(p[0], len(uniq)) for p in pairs), np.int32, count=len(pairs))
+        # (dict.fromkeys / map keep the loops over hundreds of thousands of pairs inside the interpreter's C code)
+        firsts = [p[0] for p in pairs]
+        s2 = [p[1] for p in pairs]
+        uniq = {s: k for k, s in enumerate(dict.fromkeys(firsts))}
+        s1_idx = np.fromiter(map(uniq.__getitem__, firsts), np.int32, count=len(pairs))
         # the library cleans the bytes itself (ASCII upper-case, non-alphabet -> '?', gotoh2.py:70-72); only non-ASCII text
         # goes through the reference's regular expression here, because it works on characters, not on UTF-8 bytes
         s1 = [a if a.isascii() else self.clean_sequence(a) for a in uniq]
-        s2 = [p[1] for p in pairs]
         try:
             b2, o2 = packing.pack(s2, "seq2", ascii_only=True)
         except UnicodeError:
@@ -99,7 +101,7 @@ class Aligner:
             return LazyAlignments(packing.PackedStrings(out1, out_off, out_len), packing.PackedStrings(out2, out_off, out_len), out_score)
         a = packing.unpack(out1, out_off, out_len)
         b = packing.unpack(out2, out_off, out_len)
-        return [(a[k], b[k], int(out_score[k])) for k in range(n)]
+        return list(zip(a, b, out_score.tolist()))
 
 
 class LazyAlignments:

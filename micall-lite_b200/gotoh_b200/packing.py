@@ -1,4 +1,6 @@
 """Pack Python sequences into the contiguous byte + offset arrays the C ABI takes."""
+import codecs
+
 import numpy as np
 
 
@@ -26,7 +28,7 @@ def pack(seqs, what="sequence", ascii_only=False):
         return np.zeros(0, dtype=np.uint8), off
     # fast path (hundreds of thousands of short ASCII strings): one join, one encode, lengths from len() - the per-string
     # encode / NUL check of to_bytes() costs ~0.5 us each, more than the GPU spends on an 84-aa window
-    if all(type(s) is str for s in seqs):
+    if set(map(type, seqs)) == {str}:                   # exactly str, checked without a Python frame per element
         joined = "".join(seqs)
         if joined.isascii():
             if "\0" in joined:
@@ -54,9 +56,12 @@ def out_offsets(ref_off, ref_idx, qry_off):
 
 
 def unpack(out, off, lens):
-    """Packed outputs -> list of str."""
-    buf = out.tobytes()
-    return [buf[int(off[k]):int(off[k]) + int(lens[k])].decode("latin-1") for k in range(len(lens))]
+    """Packed outputs -> list of str.  One decode of the whole buffer, then str slices over plain-int offsets: numpy
+    scalars and a per-element decode cost ~2 us per string, ten times what the slicing does."""
+    text = codecs.latin_1_decode(np.ascontiguousarray(out))[0]          # straight from the array's buffer, no bytes copy
+    n = len(lens)
+    starts = np.asarray(off[:n], dtype=np.int64)
+    return [text[a:b] for a, b in zip(starts.tolist(), (starts + np.asarray(lens, dtype=np.int64)).tolist())]
 
 
 class PackedStrings:

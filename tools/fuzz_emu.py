@@ -3,6 +3,9 @@
 (x the int32 kernels), random tables, references (incl. "$$$", IUPAC, lower case, surrounding whitespace, 1-5 rows), query
 widths 1..600 (multi-strip), gap models incl. zero penalties, the three result forms - every pair also against the oracle.
     python tools/fuzz_emu.py [seed] [trials]
+FUZZ_LONG=1: references of 200-1500 rows with tiny gap-open penalties (many rebase rows).  FUZZ_STRIPS=1: 24 pairs per
+trial with queries of 257-1800 columns (2-8 strips) through the three multi-strip forward kernels (strip dataflow, CTA per
+pair, warp per pair: GOTOH_B200_LONG=flow|cta|warp) and the int16x2-free host/device builders.
 (seed 11 of the first version found the column-0 seed bug of DESIGN.md 3.8.)"""
 import os
 import random
@@ -24,7 +27,8 @@ def main():
     trials = int(sys.argv[2]) if len(sys.argv) > 2 else 14
     rng = random.Random(seed)
     bad = total = 0
-    long_mode = os.environ.get("FUZZ_LONG") == "1"      # references up to 1500 rows, tiny gap-open: many rebase rows
+    strips_mode = os.environ.get("FUZZ_STRIPS") == "1"
+    long_mode = os.environ.get("FUZZ_LONG") == "1" or strips_mode      # references up to 1500 rows, tiny gap-open: many rebase rows
     for trial in range(trials):
         matrix = rng.choice([0, 0, 1, 2])
         if matrix == 0:
@@ -43,11 +47,27 @@ def main():
             refs.append(a)
         wide = rng.random() < 0.25
         qs, ridx = [], []
-        for k in range(160):
+        for k in range(24 if strips_mode else 160):
             r = rng.randrange(nrefs)
             a = refs[r]
-            nmax = 600 if (wide and k % 20 == 0) else 256
-            if rng.random() < 0.6:
+            nmax = 1800 if strips_mode else 600 if (wide and k % 20 == 0) else 256
+            if strips_mode and rng.random() < 0.7:
+                lo = rng.randrange(max(1, len(a) - 300))
+                q = list(a[lo:lo + rng.randint(257, 1500)].replace("$", "A"))
+                for _ in range(rng.randint(0, 6)):
+                    q[rng.randrange(len(q))] = rng.choice(alpha.replace("$", "A"))
+                for _ in range(rng.randint(0, 3)):                       # deletions and insertions of 1-40 characters
+                    p0 = rng.randrange(len(q))
+                    del q[p0:p0 + rng.randint(1, 40)]
+                for _ in range(rng.randint(0, 3)):
+                    p0 = rng.randrange(len(q) + 1)
+                    q[p0:p0] = [rng.choice(alpha.replace("$", "T")) for _ in range(rng.randint(1, 40))]
+                while len(q) < 257:
+                    q.append(rng.choice(alpha.replace("$", "T")))
+                q = "".join(q)
+            elif strips_mode:
+                q = "".join(rng.choice(alpha.replace("$", "T")) for _ in range(rng.randint(257, nmax)))
+            elif rng.random() < 0.6:
                 lo = rng.randrange(len(a))
                 q = list(a[lo:lo + rng.randint(1, 200)].replace("$$$", rng.choice(["TAG", "TAA", "TGA", "TGG"])).replace("$", "A") or "A")
                 for _ in range(rng.randint(0, 4)):
@@ -69,9 +89,13 @@ def main():
         qb, qo = packing.pack(qs)
         ri = np.asarray(ridx, np.int32)
         res = {}
-        for key, env in (("host", {"GOTOH_B200_DEVICE_PREP": "0"}), ("device", {"GOTOH_B200_DEVICE_PREP": "1"}),
-                         ("full", {"GOTOH_B200_DEVICE_PREP": "1", "GOTOH_B200_HALF": "0"}), ("int32", {"GOTOH_B200_FORCE_PATH": "32"})):
-            for v in ("GOTOH_B200_DEVICE_PREP", "GOTOH_B200_HALF", "GOTOH_B200_FORCE_PATH"):
+        paths = (("host", {"GOTOH_B200_DEVICE_PREP": "0"}), ("device", {"GOTOH_B200_DEVICE_PREP": "1"}),
+                 ("full", {"GOTOH_B200_DEVICE_PREP": "1", "GOTOH_B200_HALF": "0"}), ("int32", {"GOTOH_B200_FORCE_PATH": "32"}))
+        if strips_mode:
+            paths = (("host", {"GOTOH_B200_DEVICE_PREP": "0"}), ("device", {"GOTOH_B200_DEVICE_PREP": "1"}),
+                     ("cta", {"GOTOH_B200_LONG": "cta"}), ("warp", {"GOTOH_B200_LONG": "warp"}))
+        for key, env in paths:
+            for v in ("GOTOH_B200_DEVICE_PREP", "GOTOH_B200_HALF", "GOTOH_B200_FORCE_PATH", "GOTOH_B200_LONG"):
                 os.environ.pop(v, None)
             os.environ.update(env)
             res[key] = al.align_packed(rb, ro, ri, qb, qo, gip, gep, term, matrix)
