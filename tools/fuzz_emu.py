@@ -84,6 +84,8 @@ def main():
             ridx.append(r)
         gip = rng.choice([0, 0, 1, 3, 10, 15, 40]) if not long_mode else rng.choice([0, 0, 1, 2, 5])
         gep = rng.choice([0, 0, 1, 3, 10]) if not long_mode else rng.choice([1, 3, 10, 20, 40])
+        if strips_mode and rng.random() < 0.5:
+            gip, gep = rng.choice([(15, 3), (10, 3), (6, 1), (40, 10), (3, 0), (0, 0)])
         term = 0 if matrix == 2 else rng.choice([0, 1])
         rb, ro = packing.pack(refs)
         qb, qo = packing.pack(qs)
