@@ -1520,7 +1520,8 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
         order_cv.notify_all();
     };
     auto is_failed = [&]() { std::lock_guard<std::mutex> g(order_mu); return failed; };
-    const bool inject_fetch_failure = getenv("GOTOH_B200_TEST_FAIL_FETCH") != nullptr;    // tests: a D2H enqueue that fails
+    const char* inject_env = getenv("GOTOH_B200_TEST_FAIL_FETCH");                        // tests: a D2H enqueue that fails,
+    const int inject_fetch_slab = inject_env ? atoi(inject_env) : -1;                     // at the slab of this index
     auto builder_body = [&](int b) {
         if (cudaSetDevice(dev) != cudaSuccess) { fail_and_wake(b, fail(GOTOH_B200_ECUDA, "cudaSetDevice failed")); return; }
         int mine = 0;
@@ -1591,7 +1592,7 @@ int run_device_range(int dev, const uint8_t* ref_bytes, const int64_t* ref_off, 
                 if (failed) return;
             }
             if (trace_on()) cudaEventRecord(pl->ws->ev[1], pl->ws->stream);
-            if (inject_fetch_failure && slab == 1) rc = fail(GOTOH_B200_ECUDA, "injected result-copy failure (GOTOH_B200_TEST_FAIL_FETCH)");
+            if (slab == inject_fetch_slab) rc = fail(GOTOH_B200_ECUDA, "injected result-copy failure (GOTOH_B200_TEST_FAIL_FETCH)");
             if (!rc) rc = two_phase ? plan_fetch_a(pl) : plan_fetch(pl, out.out_ref, out.out_qry, out.out_len, out.out_score);
             if (!rc && !two_phase) {
                 if (cudaEventRecord(pl->ws->ev_done, pl->ws->stream) != cudaSuccess) rc = fail(GOTOH_B200_ECUDA, "cudaEventRecord failed");

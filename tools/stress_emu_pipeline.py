@@ -2,7 +2,9 @@
 """Stress of the one-shot call's host pipeline (slab cuts, builder threads, ordered enqueue, two-phase collector, static
 sharding over devices) on the CPU SIMT emulator: random batches under random pipeline settings, in every result form,
 alone and from several caller threads at once - each result compared byte for byte with a single-slab, single-device,
-strided run of the same batch.
+strided run of the same batch.  One round in seven injects a failing result copy at a random slab (GOTOH_B200_TEST_FAIL_FETCH):
+those calls must come back with that error (or complete correctly when the call has fewer slabs), never hang, and the rounds
+after them must be clean.
     python tools/stress_emu_pipeline.py [seed] [rounds]"""
 import os
 import random
@@ -50,9 +52,9 @@ def main():
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     rng = random.Random(seed)
-    bad = calls = 0
+    bad = calls = injected = 0
     for rnd in range(rounds):
-        for k in KNOBS:
+        for k in list(KNOBS) + ["GOTOH_B200_TEST_FAIL_FETCH"]:
             os.environ.pop(k, None)
         jobs = []
         for _ in range(rng.randint(1, 3)):                       # caller threads of this round
@@ -68,6 +70,10 @@ def main():
             if v is not None:
                 os.environ[k] = v
                 setting[k] = v
+        inject = rng.random() < 1 / 7
+        if inject:
+            os.environ["GOTOH_B200_TEST_FAIL_FETCH"] = setting["GOTOH_B200_TEST_FAIL_FETCH"] = rng.choice(["0", "1", "2", "3", "5"])
+            os.environ["GOTOH_B200_SLAB_MB"] = setting["GOTOH_B200_SLAB_MB"] = "1"
         out = [None] * len(jobs)
 
         def call(i):
@@ -93,12 +99,15 @@ def main():
             if t.is_alive():
                 print("HANG round", rnd, "job", i, jobs[i][8], "mask", jobs[i][9], setting, flush=True)
                 return 2
+            if inject and isinstance(out[i], _ffi.GotohError) and "injected" in str(out[i]):
+                injected += 1
+                continue
             if out[i] != jobs[i][7]:
                 bad += 1
                 what = out[i] if isinstance(out[i], Exception) else "%d of %d pairs differ" % (
                     sum(x != y for x, y in zip(out[i], jobs[i][7])), len(jobs[i][7]))
                 print("MISMATCH round", rnd, "job", i, jobs[i][8], "mask", jobs[i][9], setting, what, flush=True)
-    print("pipeline stress seed %d done: %d calls, %d bad" % (seed, calls, bad))
+    print("pipeline stress seed %d done: %d calls (%d ended by an injected failure), %d bad" % (seed, calls, injected, bad))
     return 1 if bad else 0
 
 
