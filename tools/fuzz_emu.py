@@ -3,7 +3,7 @@
 (x the int32 kernels), random tables, references (incl. "$$$", IUPAC, lower case, surrounding whitespace, 1-5 rows), query
 widths 1..600 (multi-strip), gap models incl. zero penalties, the three result forms - every pair also against the oracle.
     python tools/fuzz_emu.py [seed] [trials]
-FUZZ_LONG=1: references of 200-1500 rows with tiny gap-open penalties (many rebase rows).  FUZZ_STRIPS=1: 24 pairs per
+FUZZ_LONG=1: references of 200-1500 rows with tiny gap-open penalties (many rebase rows); FUZZ_TALL=1: 3 000-12 000 rows.  FUZZ_STRIPS=1: 24 pairs per
 trial with queries of 257-1800 columns (2-8 strips) through the three multi-strip forward kernels (strip dataflow, CTA per
 pair, warp per pair: GOTOH_B200_LONG=flow|cta|warp) and the int16x2-free host/device builders.
 (seed 11 of the first version found the column-0 seed bug of DESIGN.md 3.8.)"""
@@ -28,7 +28,8 @@ def main():
     rng = random.Random(seed)
     bad = total = 0
     strips_mode = os.environ.get("FUZZ_STRIPS") == "1"
-    long_mode = os.environ.get("FUZZ_LONG") == "1" or strips_mode      # references up to 1500 rows, tiny gap-open: many rebase rows
+    tall_mode = os.environ.get("FUZZ_TALL") == "1"      # 40 pairs per trial on references of 3 000-12 000 rows: hundreds of rebase rows
+    long_mode = os.environ.get("FUZZ_LONG") == "1" or strips_mode or tall_mode      # references up to 1500 rows, tiny gap-open: many rebase rows
     for trial in range(trials):
         matrix = rng.choice([0, 0, 1, 2])
         if matrix == 0:
@@ -38,7 +39,7 @@ def main():
         nrefs = rng.randint(1, 5)
         refs = []
         for _ in range(nrefs):
-            a = "".join(rng.choice(alpha) for _ in range(rng.choice([rng.randint(1, 5), rng.randint(6, 260), rng.randint(6, 260)]) if not long_mode else rng.randint(200, 1500)))
+            a = "".join(rng.choice(alpha) for _ in range(rng.choice([rng.randint(1, 5), rng.randint(6, 260), rng.randint(6, 260)]) if not long_mode else rng.randint(3000, 12000) if tall_mode else rng.randint(200, 1500)))
             if matrix == 0 and rng.random() < 0.3:
                 p = rng.randrange(len(a) + 1)
                 a = a[:p] + rng.choice(["$$$", "$$$$", "$$"]) + a[p:]
@@ -47,7 +48,7 @@ def main():
             refs.append(a)
         wide = rng.random() < 0.25
         qs, ridx = [], []
-        for k in range(24 if strips_mode else 160):
+        for k in range(24 if strips_mode else 40 if tall_mode else 160):
             r = rng.randrange(nrefs)
             a = refs[r]
             nmax = 1800 if strips_mode else 600 if (wide and k % 20 == 0) else 256
@@ -84,6 +85,8 @@ def main():
             ridx.append(r)
         gip = rng.choice([0, 0, 1, 3, 10, 15, 40]) if not long_mode else rng.choice([0, 0, 1, 2, 5])
         gep = rng.choice([0, 0, 1, 3, 10]) if not long_mode else rng.choice([1, 3, 10, 20, 40])
+        if tall_mode:
+            gep = rng.choice([1, 2, 3, 5, 8])          # 2*gip + (M+1)*gep must stay below the reference's sentinel (gotoh.cpp:284)
         if strips_mode and rng.random() < 0.5:
             gip, gep = rng.choice([(15, 3), (10, 3), (6, 1), (40, 10), (3, 0), (0, 0)])
         term = 0 if matrix == 2 else rng.choice([0, 1])
